@@ -1,0 +1,23 @@
+#pragma once
+#include "common.cuh"
+
+namespace iefvad {
+
+struct AttnTcArgs {
+  const bf16* q = nullptr;   // [B, H, T, dhp]  pre-scaled by dh^-1/2
+  const bf16* k = nullptr;   // [B, H, T, dhp]
+  const bf16* vt = nullptr;  // [B, H, dh, Tpad]
+  bf16* out = nullptr;       // [B*T, ldo], head h writes columns [h*dh, (h+1)*dh)
+  int ldo = 0;
+  int B = 0, T = 0, H = 0, dh = 0, dhp = 0, Tpad = 0;
+  const float* attn_mask = nullptr;    // optional additive [T, T]
+  const uint8_t* key_pad = nullptr;    // optional [B, T], non-zero = ignore key
+};
+
+int attn_tc(const AttnTcArgs& a, cudaStream_t stream);
+
+// fp32 plan: qkv fp32 [B*T, 3*H*dh] (bias added, q unscaled) -> out fp32 [B*T, H*dh]
+int attn_simt(const float* qkv, float* out, int B, int T, int H, int dh, const float* attn_mask,
+              const uint8_t* key_pad, cudaStream_t stream);
+
+}  // namespace iefvad

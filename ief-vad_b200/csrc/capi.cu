@@ -1,0 +1,260 @@
+// extern "C" surface declared in include/iefvad.h.
+#include "../../include/iefvad.h"
+
+#include <cmath>
+#include <new>
+
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "model.cuh"
+
+namespace iefvad {
+const char* last_error();
+}
+
+using namespace iefvad;
+
+struct iefvad_model {
+  Model impl;
+  DevBuf host_in[2], host_out[7], host_logits, host_scores;   // scratch of iefvad_model_forward_host
+};
+
+namespace {
+
+int current_sms(int* out) {
+  int dev = 0;
+  IEF_CUDA(cudaGetDevice(&dev));
+  IEF_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+  return IEFVAD_OK;
+}
+
+struct Scratch {   // stream-ordered temporaries of the stand-alone operators (test surface, not the hot path)
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t st) : s(st) {}
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, s);
+  }
+  int get(void** out, size_t bytes) {
+    IEF_CUDA(cudaMallocAsync(out, bytes ? bytes : 16, s));
+    ptrs.push_back(*out);
+    return IEFVAD_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int iefvad_abi_version(void) { return IEFVAD_ABI_VERSION; }
+const char* iefvad_last_error(void) { return iefvad::last_error(); }
+
+int iefvad_model_create(iefvad_model** out, int embed_dim, int num_heads, int num_layers, int num_refinement_steps,
+                        float lambda_ref, int noise_model, float nu, float epsilon) {
+  IEF_CHECK(out != nullptr, "iefvad_model_create: null output pointer");
+  *out = nullptr;
+  iefvad_model* m = new (std::nothrow) iefvad_model();
+  IEF_CHECK(m != nullptr, "out of host memory");
+  int rc = m->impl.init(embed_dim, num_heads, num_layers, num_refinement_steps, lambda_ref, noise_model, nu, epsilon);
+  if (rc != 0) {
+    m->impl.destroy();
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return IEFVAD_OK;
+}
+
+void iefvad_model_destroy(iefvad_model* m) {
+  if (!m) return;
+  m->impl.destroy();
+  for (auto& b : m->host_in) b.release();
+  for (auto& b : m->host_out) b.release();
+  m->host_logits.release();
+  m->host_scores.release();
+  delete m;
+}
+
+int iefvad_model_set_param(iefvad_model* m, const char* key, const float* data, int64_t numel, void* stream) {
+  IEF_CHECK(m && key && data, "iefvad_model_set_param: null argument");
+  return m->impl.set_param(key, data, numel, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_model_set_plan(iefvad_model* m, int plan) {
+  IEF_CHECK(m, "null model");
+  IEF_CHECK(plan == IEFVAD_PLAN_FP32 || (plan >= 0 && plan <= 7), "unknown precision plan %d", plan);
+  m->impl.plan = plan;
+  return IEFVAD_OK;
+}
+
+int iefvad_model_get_plan(const iefvad_model* m) { return m ? m->impl.plan : 0; }
+
+int iefvad_model_set_max_rows(iefvad_model* m, int64_t max_rows) {
+  IEF_CHECK(m && max_rows >= 1, "iefvad_model_set_max_rows: need a model and max_rows >= 1");
+  m->impl.max_rows = max_rows;
+  return IEFVAD_OK;
+}
+
+int iefvad_model_forward(iefvad_model* m, const void* img, const void* ev, int in_dtype, int64_t B, int64_t T,
+                         float* fused, float* logits, float* image_mu, float* event_mu, float* image_logvar,
+                         float* event_logvar, float* w_i, float* w_e, float* scores, void* stream) {
+  IEF_CHECK(m, "null model");
+  IEF_CHECK(in_dtype >= 0 && in_dtype <= 2, "unsupported input dtype code %d", in_dtype);
+  return m->impl.forward(img, ev, in_dtype, B, T, fused, logits, image_mu, event_mu, image_logvar, event_logvar, w_i,
+                         w_e, scores, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_model_forward_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
+                              int64_t T, float* logits_host, float* scores_host, void* stream) {
+  IEF_CHECK(m && img_host && ev_host && logits_host, "iefvad_model_forward_host: null argument");
+  IEF_CHECK(in_dtype >= 0 && in_dtype <= 2, "unsupported input dtype code %d", in_dtype);
+  IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0 || T == 0) return IEFVAD_OK;
+  const int D = m->impl.D;
+  const size_t es = (in_dtype == IEFVAD_F32) ? 4 : 2;
+  int64_t slabB = m->impl.max_rows / T;
+  if (slabB < 1) slabB = 1;
+  if (slabB > B) slabB = B;
+  const size_t rows = size_t(slabB) * T;
+  for (auto& b : m->host_in) IEF_TRY(b.reserve(rows * D * es));
+  for (auto& b : m->host_out) IEF_TRY(b.reserve(rows * D * 4));
+  IEF_TRY(m->host_logits.reserve(rows * 4));
+  IEF_TRY(m->host_scores.reserve(rows * 4));
+  for (int64_t b0 = 0; b0 < B; b0 += slabB) {
+    const int64_t Bs = (B - b0 < slabB) ? (B - b0) : slabB;
+    const size_t r0 = size_t(b0) * T, nr = size_t(Bs) * T;
+    IEF_CUDA(cudaMemcpyAsync(m->host_in[0].p, static_cast<const uint8_t*>(img_host) + r0 * D * es, nr * D * es,
+                             cudaMemcpyHostToDevice, st));
+    IEF_CUDA(cudaMemcpyAsync(m->host_in[1].p, static_cast<const uint8_t*>(ev_host) + r0 * D * es, nr * D * es,
+                             cudaMemcpyHostToDevice, st));
+    float* o[7];
+    for (int i = 0; i < 7; ++i) o[i] = m->host_out[i].as<float>();
+    IEF_TRY(m->impl.forward(m->host_in[0].p, m->host_in[1].p, in_dtype, Bs, T, o[0], m->host_logits.as<float>(), o[1],
+                            o[2], o[3], o[4], o[5], o[6], scores_host ? m->host_scores.as<float>() : nullptr, st));
+    IEF_CUDA(cudaMemcpyAsync(logits_host + r0, m->host_logits.p, nr * 4, cudaMemcpyDeviceToHost, st));
+    if (scores_host) IEF_CUDA(cudaMemcpyAsync(scores_host + r0, m->host_scores.p, nr * 4, cudaMemcpyDeviceToHost, st));
+  }
+  IEF_CUDA(cudaStreamSynchronize(st));
+  return IEFVAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ operators
+
+int iefvad_fuse(const float* mu_i, const float* mu_e, const float* logvar_i, const float* logvar_e, int64_t n,
+                float factor, float epsilon, float* w_i, float* w_e, float* fused, void* stream) {
+  IEF_CHECK(mu_i && mu_e && logvar_i && logvar_e && w_i && w_e, "iefvad_fuse: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return fuse(mu_i, mu_e, logvar_i, logvar_e, n, factor, epsilon, w_i, w_e, fused, nullptr, nullptr, sms,
+              static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_layernorm(const float* x, int64_t rows, int dim, const float* w1, const float* b1, const float* w2,
+                     const float* b2, float eps, float* out, void* stream) {
+  IEF_CHECK(x && out, "iefvad_layernorm: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return layernorm(x, rows, dim, w1, b1, w2, b2, eps, out, nullptr, nullptr, sms, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_linear(const float* x, const float* w, const float* bias, const float* resid, float alpha, int act,
+                  int64_t rows, int in_f, int out_f, int plan, int tile_n, float* out, void* stream) {
+  IEF_CHECK(x && w && out, "iefvad_linear: null argument");
+  IEF_CHECK(rows >= 0 && rows < (1LL << 31), "iefvad_linear: bad row count");
+  IEF_CHECK(plan >= -1 && plan <= 1, "iefvad_linear: plan must be -1 (fp32), 0 (bf16) or 1 (split-bf16)");
+  if (rows == 0) return IEFVAD_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  EpiParams ep;
+  ep.bias = bias; ep.act = act; ep.resid = resid; ep.ld_resid = out_f; ep.alpha = alpha;
+  ep.out_f32 = out; ep.ld_f32 = out_f;
+  if (plan < 0) return gemm_simt(x, in_f, w, in_f, int(rows), out_f, in_f, ep, st);
+  IEF_CHECK((rows * in_f) % 8 == 0 && (int64_t(out_f) * in_f) % 8 == 0, "iefvad_linear: sizes must be multiples of 8");
+  Scratch sc(st);
+  void *xh, *xl, *wh, *wl;
+  IEF_TRY(sc.get(&xh, size_t(rows) * in_f * 2));
+  IEF_TRY(sc.get(&xl, size_t(rows) * in_f * 2));
+  IEF_TRY(sc.get(&wh, size_t(out_f) * in_f * 2));
+  IEF_TRY(sc.get(&wl, size_t(out_f) * in_f * 2));
+  IEF_TRY(ingest(x, IEFVAD_DT_F32, rows * in_f, nullptr, (bf16*)xh, (bf16*)xl, sms, st));
+  IEF_TRY(ingest(w, IEFVAD_DT_F32, int64_t(out_f) * in_f, nullptr, (bf16*)wh, (bf16*)wl, sms, st));
+  GemmTcArgs g;
+  g.A_hi = (bf16*)xh; g.A_lo = (bf16*)xl; g.W_hi = (bf16*)wh; g.W_lo = (bf16*)wl;
+  g.M = int(rows); g.N = out_f; g.K = in_f; g.lda = in_f; g.ldw = in_f; g.nsplit = plan == 1 ? 3 : 1;
+  g.force_bn = tile_n;
+  return gemm_tc(g, ep, sms, st);
+}
+
+int iefvad_mha(const float* x, const float* in_w, const float* in_b, const float* out_w, const float* out_b,
+               int64_t B, int64_t T, int D, int num_heads, const float* attn_mask, const uint8_t* key_padding_mask,
+               int plan, float* out, void* stream) {
+  IEF_CHECK(x && in_w && in_b && out_w && out_b && out, "iefvad_mha: null argument");
+  IEF_CHECK(num_heads > 0 && D % num_heads == 0, "iefvad_mha: heads must divide D");
+  IEF_CHECK(plan >= -1 && plan <= 1, "iefvad_mha: plan must be -1, 0 or 1");
+  IEF_CHECK(B >= 0 && T >= 0 && B * T < (1LL << 31), "iefvad_mha: bad sizes");
+  if (B == 0 || T == 0) return IEFVAD_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  const int64_t M = B * T;
+  const int dh = D / num_heads, dhp = (dh + 63) / 64 * 64, Tpad = int((T + 7) / 8 * 8);
+  Scratch sc(st);
+  if (plan < 0) {
+    void *qkv, *ctx;
+    IEF_TRY(sc.get(&qkv, size_t(M) * 3 * D * 4));
+    IEF_TRY(sc.get(&ctx, size_t(M) * D * 4));
+    EpiParams e1;
+    e1.bias = in_b; e1.out_f32 = (float*)qkv; e1.ld_f32 = 3 * D;
+    IEF_TRY(gemm_simt(x, D, in_w, D, int(M), 3 * D, D, e1, st));
+    IEF_TRY(attn_simt((float*)qkv, (float*)ctx, int(B), int(T), num_heads, dh, attn_mask, key_padding_mask, st));
+    EpiParams e2;
+    e2.bias = out_b; e2.out_f32 = out; e2.ld_f32 = D;
+    return gemm_simt((float*)ctx, D, out_w, D, int(M), D, D, e2, st);
+  }
+  IEF_CHECK(D % 64 == 0, "iefvad_mha: tensor-core plans need D %% 64 == 0");
+  void *xh, *xl, *iwh, *iwl, *owh, *owl, *q, *k, *vt, *ctx;
+  IEF_TRY(sc.get(&xh, size_t(M) * D * 2));
+  IEF_TRY(sc.get(&xl, size_t(M) * D * 2));
+  IEF_TRY(sc.get(&iwh, size_t(3) * D * D * 2));
+  IEF_TRY(sc.get(&iwl, size_t(3) * D * D * 2));
+  IEF_TRY(sc.get(&owh, size_t(D) * D * 2));
+  IEF_TRY(sc.get(&owl, size_t(D) * D * 2));
+  IEF_TRY(sc.get(&q, size_t(M) * num_heads * dhp * 2));
+  IEF_TRY(sc.get(&k, size_t(M) * num_heads * dhp * 2));
+  IEF_TRY(sc.get(&vt, size_t(B) * num_heads * dh * Tpad * 2));
+  IEF_TRY(sc.get(&ctx, size_t(M) * D * 2));
+  IEF_TRY(ingest(x, IEFVAD_DT_F32, M * D, nullptr, (bf16*)xh, (bf16*)xl, sms, st));
+  IEF_TRY(ingest(in_w, IEFVAD_DT_F32, 3LL * D * D, nullptr, (bf16*)iwh, (bf16*)iwl, sms, st));
+  IEF_TRY(ingest(out_w, IEFVAD_DT_F32, 1LL * D * D, nullptr, (bf16*)owh, (bf16*)owl, sms, st));
+  EpiParams e1;
+  e1.mode = EPI_QKV; e1.bias = in_b; e1.q = (bf16*)q; e1.k = (bf16*)k; e1.vt = (bf16*)vt;
+  e1.T = int(T); e1.H = num_heads; e1.dh = dh; e1.dhp = dhp; e1.Tpad = Tpad; e1.D = D;
+  e1.qscale = 1.0f / sqrtf(float(dh));
+  GemmTcArgs g1;
+  g1.A_hi = (bf16*)xh; g1.A_lo = (bf16*)xl; g1.W_hi = (bf16*)iwh; g1.W_lo = (bf16*)iwl;
+  g1.M = int(M); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = plan == 1 ? 3 : 1;
+  IEF_TRY(gemm_tc(g1, e1, sms, st));
+  AttnTcArgs at;
+  at.q = (bf16*)q; at.k = (bf16*)k; at.vt = (bf16*)vt; at.out = (bf16*)ctx; at.ldo = D;
+  at.B = int(B); at.T = int(T); at.H = num_heads; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
+  at.attn_mask = attn_mask; at.key_pad = key_padding_mask;
+  IEF_TRY(attn_tc(at, st));
+  EpiParams e2;
+  e2.bias = out_b; e2.out_f32 = out; e2.ld_f32 = D;
+  GemmTcArgs g2;
+  g2.A_hi = (bf16*)ctx; g2.W_hi = (bf16*)owh; g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
+  return gemm_tc(g2, e2, sms, st);
+}
+
+int iefvad_classifier(const float* x, int64_t rows, int dim, const float* w, const float* bias, float* logits,
+                      float* scores, void* stream) {
+  IEF_CHECK(x && w && bias && logits, "iefvad_classifier: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return classifier(x, rows, dim, w, bias, logits, scores, sms, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

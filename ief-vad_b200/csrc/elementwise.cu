@@ -1,0 +1,261 @@
+// HBM-bound kernels of the forward: input ingest, LayerNorm (single / double), the uncertainty-weighted
+// fusion (model/imf_vad.py:130-144) and the 768->1 classifier (model/imf_vad.py:150).  All fp32 IEEE
+// arithmetic (no fast-math), 128-bit global accesses, grids sized in multiples of the SM count.
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace iefvad {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__host__ int grid_for(long long work_items, int num_sms, int per_sm = 8) {
+  long long blocks = (work_items + kThreads - 1) / kThreads;
+  long long cap = (long long)num_sms * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ---------------------------------------------------------------- ingest: any float dtype -> fp32 (+bf16 hi)
+template <typename Tin>
+__device__ __forceinline__ void load8(const Tin* p, float* v);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float* v) {
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float* v) {
+  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float* v) {
+  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
+template <typename Tin>
+__global__ void __launch_bounds__(kThreads)
+ingest_kernel(const Tin* __restrict__ in, long long n8, float* __restrict__ out_f32, bf16* __restrict__ out_hi,
+              bf16* __restrict__ out_lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8<Tin>(in + i * 8, v);
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + i * 8);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bf16 ah = __float2bfloat16_rn(v[2 * q]), bh = __float2bfloat16_rn(v[2 * q + 1]);
+      hi[q] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+      lo[q] = pack_bf16x2(v[2 * q] - __bfloat162float(ah), v[2 * q + 1] - __bfloat162float(bh));
+    }
+    if (out_hi) *reinterpret_cast<uint4*>(out_hi + i * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + i * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm: one warp per row, row in registers
+template <int NV>   // D = 128 * NV
+__global__ void __launch_bounds__(kThreads)
+layernorm_kernel(const float* __restrict__ x, long long M, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, const float* __restrict__ b2, float eps, float* __restrict__ out_f32,
+                 bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  constexpr int D = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+    float v[NV * 4];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 t = xr[lane + 32 * i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const float* w = pass ? w2 : w1;
+      const float* b = pass ? b2 : b1;
+      if (w == nullptr) break;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV * 4; ++i) s += v[i];
+      const float mean = warp_sum(s) * (1.f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV * 4; ++i) {
+        const float c = v[i] - mean;
+        q = fmaf(c, c, q);
+      }
+      const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / D) + eps);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+        v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * wv.x + bv.x;
+        v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * wv.y + bv.y;
+        v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * wv.z + bv.z;
+        v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * wv.w + bv.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const long long off = row * D + (lane + 32 * i) * 4;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (out_hi) {
+        bf16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_bf16(v[4 * i + e], h[e], l[e]);
+        *reinterpret_cast<uint2*>(out_hi + off) = *reinterpret_cast<uint2*>(h);
+        if (out_lo) *reinterpret_cast<uint2*>(out_lo + off) = *reinterpret_cast<uint2*>(l);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- uncertainty-weighted fusion
+__global__ void __launch_bounds__(kThreads)
+fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, const float4* __restrict__ lv_i,
+            const float4* __restrict__ lv_e, long long n4, float factor, float eps, float4* __restrict__ w_i,
+            float4* __restrict__ w_e, float4* __restrict__ fused, bf16* __restrict__ fused_hi,
+            bf16* __restrict__ fused_lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(mu_i + i), b = __ldcs(mu_e + i), c = __ldcs(lv_i + i), d = __ldcs(lv_e + i);
+    const float mi[4] = {a.x, a.y, a.z, a.w}, me[4] = {b.x, b.y, b.z, b.w};
+    const float li[4] = {c.x, c.y, c.z, c.w}, le[4] = {d.x, d.y, d.z, d.w};
+    float wi[4], we[4], f[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // exact op order of model/imf_vad.py:134-144, every product / sum rounded separately like ATen
+      const float ri = __fmul_rn(factor, expf(-li[e]));
+      const float re = __fmul_rn(factor, expf(-le[e]));
+      const float den = __fadd_rn(__fadd_rn(ri, re), eps);
+      wi[e] = __fdiv_rn(ri, den);
+      we[e] = __fdiv_rn(re, den);
+      f[e] = __fadd_rn(__fmul_rn(wi[e], mi[e]), __fmul_rn(we[e], me[e]));
+    }
+    __stcs(w_i + i, make_float4(wi[0], wi[1], wi[2], wi[3]));
+    __stcs(w_e + i, make_float4(we[0], we[1], we[2], we[3]));
+    if (fused) fused[i] = make_float4(f[0], f[1], f[2], f[3]);
+    if (fused_hi) {
+      bf16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_bf16(f[e], h[e], l[e]);
+      *reinterpret_cast<uint2*>(fused_hi + i * 4) = *reinterpret_cast<uint2*>(h);
+      if (fused_lo) *reinterpret_cast<uint2*>(fused_lo + i * 4) = *reinterpret_cast<uint2*>(l);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- classifier: warp-per-row fp32 dot product
+__global__ void __launch_bounds__(kThreads)
+classifier_kernel(const float* __restrict__ x, long long M, int D, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ logits, float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float b = __ldg(bias);
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float s = 0.f;
+    for (int i = lane; i < D / 4; i += 32) {
+      const float4 xv = xr[i];
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + i);
+      s = fmaf(xv.x, wv.x, s);
+      s = fmaf(xv.y, wv.y, s);
+      s = fmaf(xv.z, wv.z, s);
+      s = fmaf(xv.w, wv.w, s);
+    }
+    s = warp_sum(s) + b;
+    if (lane == 0) {
+      logits[row] = s;
+      if (scores) scores[row] = 1.f / (1.f + expf(-s));
+    }
+  }
+}
+
+}  // namespace
+
+int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms,
+           cudaStream_t stream) {
+  IEF_CHECK(n % 8 == 0, "ingest: element count %lld must be a multiple of 8", n);
+  if (n == 0) return IEFVAD_OK;
+  const long long n8 = n / 8;
+  const int grid = grid_for(n8, num_sms);
+  switch (dtype) {
+    case IEFVAD_DT_F32:
+      ingest_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(in), n8, out_f32, out_hi, out_lo);
+      break;
+    case IEFVAD_DT_F16:
+      ingest_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half*>(in), n8, out_f32, out_hi, out_lo);
+      break;
+    case IEFVAD_DT_BF16:
+      ingest_kernel<bf16><<<grid, kThreads, 0, stream>>>(static_cast<const bf16*>(in), n8, out_f32, out_hi, out_lo);
+      break;
+    default:
+      set_error("ingest: unsupported dtype code %d (0 = f32, 1 = f16, 2 = bf16)", dtype);
+      return IEFVAD_ERR_INVALID;
+  }
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int layernorm(const float* x, long long M, int D, const float* w1, const float* b1, const float* w2, const float* b2,
+              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream) {
+  IEF_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: D=%d must be a multiple of 128 in [128, 1024]", D);
+  IEF_CHECK(w1 && b1 && (w2 == nullptr) == (b2 == nullptr), "layernorm: bad affine pointers");
+  if (M == 0) return IEFVAD_OK;
+  const int grid = grid_for(M * 32, num_sms);
+#define IEF_LN(NV)                                                                                              \
+  case NV:                                                                                                      \
+    layernorm_kernel<NV><<<grid, kThreads, 0, stream>>>(x, M, w1, b1, w2, b2, eps, out_f32, out_hi, out_lo);  \
+    break;
+  switch (D / 128) {
+    IEF_LN(1) IEF_LN(2) IEF_LN(3) IEF_LN(4) IEF_LN(5) IEF_LN(6) IEF_LN(7) IEF_LN(8)
+  }
+#undef IEF_LN
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long n, float factor,
+         float eps, float* w_i, float* w_e, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
+         cudaStream_t stream) {
+  IEF_CHECK(n % 4 == 0, "fuse: element count %lld must be a multiple of 4", n);
+  if (n == 0) return IEFVAD_OK;
+  const long long n4 = n / 4;
+  fuse_kernel<<<grid_for(n4, num_sms), kThreads, 0, stream>>>(
+      reinterpret_cast<const float4*>(mu_i), reinterpret_cast<const float4*>(mu_e),
+      reinterpret_cast<const float4*>(lv_i), reinterpret_cast<const float4*>(lv_e), n4, factor, eps,
+      reinterpret_cast<float4*>(w_i), reinterpret_cast<float4*>(w_e), reinterpret_cast<float4*>(fused), fused_hi,
+      fused_lo);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int classifier(const float* x, long long M, int D, const float* w, const float* bias, float* logits, float* scores,
+               int num_sms, cudaStream_t stream) {
+  IEF_CHECK(D % 4 == 0, "classifier: D=%d must be a multiple of 4", D);
+  if (M == 0) return IEFVAD_OK;
+  classifier_kernel<<<grid_for(M * 32, num_sms), kThreads, 0, stream>>>(x, M, D, w, bias, logits, scores);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+}  // namespace iefvad

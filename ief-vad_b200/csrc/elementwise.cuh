@@ -1,0 +1,25 @@
+#pragma once
+#include "common.cuh"
+
+namespace iefvad {
+
+enum : int { IEFVAD_DT_F32 = 0, IEFVAD_DT_F16 = 1, IEFVAD_DT_BF16 = 2 };
+
+// in (f32 / f16 / bf16, n elements, n % 8 == 0) -> optional fp32 copy, optional bf16 hi, optional bf16 lo
+int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms,
+           cudaStream_t stream);
+
+// out = LN(x; w1, b1) or LN(LN(x; w1, b1); w2, b2) when w2 != null.  x [M, D] fp32.
+int layernorm(const float* x, long long M, int D, const float* w1, const float* b1, const float* w2, const float* b2,
+              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream);
+
+// model/imf_vad.py:130-144.  n elements; fused / fused_hi / fused_lo optional.
+int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long n, float factor,
+         float eps, float* w_i, float* w_e, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
+         cudaStream_t stream);
+
+// logits[row] = x[row, :] . w + bias;  scores (optional) = sigmoid(logits)
+int classifier(const float* x, long long M, int D, const float* w, const float* bias, float* logits, float* scores,
+               int num_sms, cudaStream_t stream);
+
+}  // namespace iefvad

@@ -1,0 +1,26 @@
+// Internal C++ interface of the two GEMM engines (tcgen05 bf16 and fp32 SIMT).
+#pragma once
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace iefvad {
+
+struct GemmTcArgs {
+  const bf16* A_hi = nullptr;  // [M, lda]  activations (K-major)
+  const bf16* A_lo = nullptr;  // residual of the bf16 rounding, only for nsplit == 3
+  const bf16* W_hi = nullptr;  // [N, ldw]  nn.Linear weight layout (K-major)
+  const bf16* W_lo = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldw = 0;
+  int nsplit = 1;              // 1: plain bf16;  3: hi.hi + hi.lo + lo.hi
+  int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256 (tests, tuning)
+};
+
+int gemm_tc(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_t stream);
+
+// fp32 FFMA GEMM with the same epilogue: the "fp32 plan" (1e-5 class) and the on-device yardstick
+// the tcgen05 path is debugged against.  A [M, lda] fp32, W [N, ldw] fp32.
+int gemm_simt(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const EpiParams& ep,
+              cudaStream_t stream);
+
+}  // namespace iefvad

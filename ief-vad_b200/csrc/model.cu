@@ -1,0 +1,332 @@
+// The IEF-VAD forward (model/imf_vad.py:109-161) as a sequence of sm_100a kernels.
+#include "model.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace iefvad {
+
+int DevBuf::reserve(size_t need) {
+  if (need <= bytes) return IEFVAD_OK;
+  if (p) {
+    IEF_CUDA(cudaFree(p));
+    p = nullptr;
+    bytes = 0;
+  }
+  IEF_CUDA(cudaMalloc(&p, need));
+  bytes = need;
+  return IEFVAD_OK;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+namespace {
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}  // namespace
+
+int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, float lambda, int noise_model, float nu,
+                float epsilon) {
+  IEF_CHECK(embed_dim >= 128 && embed_dim % 128 == 0 && embed_dim <= 1024,
+            "embed_dim=%d unsupported: need a multiple of 128 in [128, 1024]", embed_dim);
+  IEF_CHECK(num_heads > 0 && embed_dim % num_heads == 0, "num_heads=%d must divide embed_dim=%d", num_heads, embed_dim);
+  D = embed_dim; H = num_heads; L = layers; R = refine_steps;
+  dh = D / H;
+  IEF_CHECK(dh == 32 || dh == 64 || dh == 96 || dh == 128, "head dim %d unsupported (32, 64, 96, 128)", dh);
+  dhp = (dh + 63) / 64 * 64;
+  IEF_CHECK(L >= 0 && R >= 0, "negative layer / refinement count");
+  lambda_ref = lambda;
+  eps = epsilon;
+  if (noise_model == 0) factor = 1.f;                                  // Gaussian, model/imf_vad.py:130-132
+  else if (noise_model == 1) factor = (nu + 1.f) / nu;                 // StudentT, :133-136
+  else { set_error("Unsupported noise_model. Choose 'Gaussian' or 'StudentT'."); return IEFVAD_ERR_INVALID; }
+  IEF_CUDA(cudaGetDevice(&device));
+  IEF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+
+  // ---- carve one fp32 arena (+ bf16 hi / lo arenas mirroring the weight matrices)
+  struct Want { std::string key; long long numel; bool is_weight; float** dst; bf16** hi; bf16** lo; };
+  std::vector<Want> wants;
+  const char* mods[2] = {"image", "event"};
+  for (int m = 0; m < 2; ++m) {
+    in_proj[m].assign(L, Linear());
+    out_proj[m].assign(L, Linear());
+    ln_w[m].assign(L, nullptr);
+    ln_b[m].assign(L, nullptr);
+  }
+  ref1.assign(R, Linear());
+  ref2.assign(R, Linear());
+  char buf[160];
+  for (int m = 0; m < 2; ++m) {
+    for (int i = 0; i < L; ++i) {
+      Linear& ip = in_proj[m][i];
+      Linear& op = out_proj[m][i];
+      ip.out = 3 * D; ip.in = D; op.out = D; op.in = D;
+      snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.in_proj_weight", mods[m], i);
+      wants.push_back({buf, 3LL * D * D, true, &ip.w, &ip.w_hi, &ip.w_lo});
+      snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.in_proj_bias", mods[m], i);
+      wants.push_back({buf, 3LL * D, false, &ip.b, nullptr, nullptr});
+      snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.out_proj.weight", mods[m], i);
+      wants.push_back({buf, 1LL * D * D, true, &op.w, &op.w_hi, &op.w_lo});
+      snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.out_proj.bias", mods[m], i);
+      wants.push_back({buf, D, false, &op.b, nullptr, nullptr});
+      snprintf(buf, sizeof(buf), "temporal.%s_norms.%d.weight", mods[m], i);
+      wants.push_back({buf, D, false, &ln_w[m][i], nullptr, nullptr});
+      snprintf(buf, sizeof(buf), "temporal.%s_norms.%d.bias", mods[m], i);
+      wants.push_back({buf, D, false, &ln_b[m][i], nullptr, nullptr});
+    }
+    snprintf(buf, sizeof(buf), "temporal.whiten_%s.weight", mods[m]);
+    wants.push_back({buf, D, false, &whiten_w[m], nullptr, nullptr});
+    snprintf(buf, sizeof(buf), "temporal.whiten_%s.bias", mods[m]);
+    wants.push_back({buf, D, false, &whiten_b[m], nullptr, nullptr});
+    heads[m].out = 2 * D; heads[m].in = D;
+    // mu and logvar of one modality share their input: stored as one [2D, D] matrix (rows [0,D) = mu)
+    wants.push_back({std::string("@heads_w.") + mods[m], 2LL * D * D, true, &heads[m].w, &heads[m].w_hi, &heads[m].w_lo});
+    wants.push_back({std::string("@heads_b.") + mods[m], 2LL * D, false, &heads[m].b, nullptr, nullptr});
+  }
+  for (int i = 0; i < R; ++i) {
+    ref1[i].out = ref1[i].in = ref2[i].out = ref2[i].in = D;
+    snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.0.weight", i);
+    wants.push_back({buf, 1LL * D * D, true, &ref1[i].w, &ref1[i].w_hi, &ref1[i].w_lo});
+    snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.0.bias", i);
+    wants.push_back({buf, D, false, &ref1[i].b, nullptr, nullptr});
+    snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.2.weight", i);
+    wants.push_back({buf, 1LL * D * D, true, &ref2[i].w, &ref2[i].w_hi, &ref2[i].w_lo});
+    snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.2.bias", i);
+    wants.push_back({buf, D, false, &ref2[i].b, nullptr, nullptr});
+  }
+  wants.push_back({"temporal.classifier.weight", D, false, &cls_w, nullptr, nullptr});
+  wants.push_back({"temporal.classifier.bias", 1, false, &cls_b, nullptr, nullptr});
+
+  size_t f32_elems = 0, bf_elems = 0;
+  for (auto& w : wants) {
+    f32_elems += align_up(size_t(w.numel), 64);
+    if (w.is_weight) bf_elems += align_up(size_t(w.numel), 64);
+  }
+  IEF_TRY(params_f32.reserve(f32_elems * sizeof(float)));
+  IEF_TRY(params_hi.reserve(bf_elems * sizeof(bf16)));
+  IEF_TRY(params_lo.reserve(bf_elems * sizeof(bf16)));
+  IEF_CUDA(cudaMemset(params_f32.p, 0, params_f32.bytes));
+  size_t fo = 0, bo = 0;
+  for (auto& w : wants) {
+    *w.dst = params_f32.as<float>() + fo;
+    fo += align_up(size_t(w.numel), 64);
+    ParamSlot s;
+    s.dst = *w.dst;
+    s.numel = w.numel;
+    if (w.is_weight) {
+      *w.hi = params_hi.as<bf16>() + bo;
+      *w.lo = params_lo.as<bf16>() + bo;
+      s.hi = *w.hi;
+      s.lo = *w.lo;
+      bo += align_up(size_t(w.numel), 64);
+    }
+    slots[w.key] = s;
+  }
+  // the four head Linears alias halves of the packed [2D, D] matrices
+  for (int m = 0; m < 2; ++m) {
+    const ParamSlot& hw = slots[std::string("@heads_w.") + mods[m]];
+    const ParamSlot& hb = slots[std::string("@heads_b.") + mods[m]];
+    const char* kinds[2] = {"mu", "logvar"};
+    for (int k = 0; k < 2; ++k) {
+      ParamSlot sw;
+      sw.dst = hw.dst + (long long)k * D * D; sw.numel = 1LL * D * D;
+      sw.hi = hw.hi + (long long)k * D * D;   sw.lo = hw.lo + (long long)k * D * D;
+      snprintf(buf, sizeof(buf), "temporal.%s_%s.weight", mods[m], kinds[k]);
+      slots[buf] = sw;
+      ParamSlot sb;
+      sb.dst = hb.dst + (long long)k * D; sb.numel = D;
+      snprintf(buf, sizeof(buf), "temporal.%s_%s.bias", mods[m], kinds[k]);
+      slots[buf] = sb;
+    }
+    slots.erase(std::string("@heads_w.") + mods[m]);
+    slots.erase(std::string("@heads_b.") + mods[m]);
+  }
+  return IEFVAD_OK;
+}
+
+int Model::set_param(const char* key, const float* dptr, long long numel, cudaStream_t stream) {
+  auto it = slots.find(key);
+  IEF_CHECK(it != slots.end(), "unexpected parameter key '%s'", key);
+  ParamSlot& s = it->second;
+  IEF_CHECK(s.numel == numel, "parameter '%s': expected %lld elements, got %lld", key, s.numel, numel);
+  IEF_CUDA(cudaMemcpyAsync(s.dst, dptr, size_t(numel) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if (s.hi) IEF_TRY(ingest(s.dst, IEFVAD_DT_F32, numel, nullptr, s.hi, s.lo, num_sms, stream));
+  s.loaded = true;
+  return IEFVAD_OK;
+}
+
+int Model::check_loaded() const {
+  for (auto& kv : slots)
+    if (!kv.second.loaded) {
+      set_error("parameter '%s' was never uploaded (iefvad_model_set_param)", kv.first.c_str());
+      return IEFVAD_ERR_STATE;
+    }
+  return IEFVAD_OK;
+}
+
+int Model::reserve_workspace(long long rows, int B, int T, bool fp32_plan) {
+  const size_t act = size_t(rows) * D;
+  IEF_TRY(x32.reserve(act * 4));
+  IEF_TRY(y32.reserve(act * 4));
+  if (!fp32_plan) {
+    IEF_TRY(a_hi.reserve(act * 2));
+    IEF_TRY(a_lo.reserve(act * 2));
+    IEF_TRY(h_hi.reserve(act * 2));
+    IEF_TRY(h_lo.reserve(act * 2));
+    const int Tpad = (T + 7) / 8 * 8;
+    IEF_TRY(qb.reserve(size_t(B) * H * T * dhp * 2));
+    IEF_TRY(kb.reserve(size_t(B) * H * T * dhp * 2));
+    IEF_TRY(vtb.reserve(size_t(B) * H * dh * Tpad * 2));
+  } else {
+    IEF_TRY(qkv32.reserve(act * 3 * 4));
+    IEF_TRY(attn32.reserve(act * 4));
+    IEF_TRY(h32.reserve(act * 4));
+  }
+  return IEFVAD_OK;
+}
+
+int Model::forward(const void* img, const void* ev, int in_dtype, long long B, long long T, float* fused, float* logits,
+                   float* image_mu, float* event_mu, float* image_logvar, float* event_logvar, float* w_i, float* w_e,
+                   float* scores, cudaStream_t stream) {
+  IEF_TRY(check_loaded());
+  IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
+  IEF_CHECK(img && ev && fused && logits && image_mu && event_mu && image_logvar && event_logvar && w_i && w_e,
+            "forward: null tensor pointer");
+  if (B == 0 || T == 0) return IEFVAD_OK;
+  IEF_CHECK(T <= (1 << 24), "T=%lld too long", T);
+  const bool fp32_plan = plan < 0;
+  const size_t in_esize = (in_dtype == IEFVAD_DT_F32) ? 4 : 2;
+  long long slabB = max_rows / T;
+  if (slabB < 1) slabB = 1;
+  if (slabB > B) slabB = B;
+  if (slabB > 65535) slabB = 65535;
+  IEF_TRY(reserve_workspace(slabB * T, int(slabB), int(T), fp32_plan));
+  const int Tpad = int((T + 7) / 8 * 8);
+  const float qscale = 1.0f / sqrtf(float(dh));
+  float* mu_out[2] = {image_mu, event_mu};
+  float* lv_out[2] = {image_logvar, event_logvar};
+  const void* inputs[2] = {img, ev};
+
+  for (long long b0 = 0; b0 < B; b0 += slabB) {
+    const int Bs = int((B - b0 < slabB) ? (B - b0) : slabB);
+    const long long M = (long long)Bs * T;
+    IEF_CHECK(M < (1LL << 31), "slab of %lld rows exceeds 2^31", M);
+    const long long row0 = b0 * T;
+    for (int m = 0; m < 2; ++m) {
+      const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + size_t(row0) * D * in_esize;
+      IEF_TRY(ingest(in, in_dtype, M * D, x32.as<float>(), fp32_plan ? nullptr : a_hi.as<bf16>(),
+                     (!fp32_plan && (plan & PLAN_SPLIT_ENCODER)) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+      for (int i = 0; i < L; ++i) {                                   // model/imf_vad.py:114-116 / :120-122
+        const Linear& ip = in_proj[m][i];
+        const Linear& op = out_proj[m][i];
+        const bool last = (i == L - 1);
+        if (fp32_plan) {
+          EpiParams e1;
+          e1.bias = ip.b; e1.out_f32 = qkv32.as<float>(); e1.ld_f32 = 3 * D;
+          IEF_TRY(gemm_simt(x32.as<float>(), D, ip.w, D, int(M), 3 * D, D, e1, stream));
+          IEF_TRY(attn_simt(qkv32.as<float>(), attn32.as<float>(), Bs, int(T), H, dh, nullptr, nullptr, stream));
+          EpiParams e2;
+          e2.bias = op.b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.out_f32 = y32.as<float>(); e2.ld_f32 = D;
+          IEF_TRY(gemm_simt(attn32.as<float>(), D, op.w, D, int(M), D, D, e2, stream));
+          IEF_TRY(layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
+                            last ? whiten_b[m] : nullptr, 1e-5f, x32.as<float>(), nullptr, nullptr, num_sms, stream));
+        } else {
+          const bool sp = (plan & PLAN_SPLIT_ENCODER) != 0;
+          EpiParams e1;
+          e1.mode = EPI_QKV; e1.bias = ip.b; e1.q = qb.as<bf16>(); e1.k = kb.as<bf16>(); e1.vt = vtb.as<bf16>();
+          e1.T = int(T); e1.H = H; e1.dh = dh; e1.dhp = dhp; e1.Tpad = Tpad; e1.D = D; e1.qscale = qscale;
+          GemmTcArgs g1;
+          g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = ip.w_hi; g1.W_lo = ip.w_lo;
+          g1.M = int(M); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1;
+          IEF_TRY(gemm_tc(g1, e1, num_sms, stream));
+          AttnTcArgs at;
+          at.q = qb.as<bf16>(); at.k = kb.as<bf16>(); at.vt = vtb.as<bf16>(); at.out = h_hi.as<bf16>(); at.ldo = D;
+          at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
+          IEF_TRY(attn_tc(at, stream));
+          EpiParams e2;
+          e2.bias = op.b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.out_f32 = y32.as<float>(); e2.ld_f32 = D;
+          GemmTcArgs g2;
+          g2.A_hi = h_hi.as<bf16>(); g2.W_hi = op.w_hi; g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
+          IEF_TRY(gemm_tc(g2, e2, num_sms, stream));
+          // LN_i (+ whitening LN after the last layer, :117/:123); bf16 hi(/lo) feed the next GEMM
+          const bool need_lo = last ? (plan & PLAN_SPLIT_HEADS) != 0 : sp;
+          IEF_TRY(layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
+                            last ? whiten_b[m] : nullptr, 1e-5f, last ? nullptr : x32.as<float>(), a_hi.as<bf16>(),
+                            need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+        }
+      }
+      if (L == 0) {
+        // no attention layers: only the whitening LN (model/imf_vad.py:117)
+        IEF_TRY(layernorm(x32.as<float>(), M, D, whiten_w[m], whiten_b[m], nullptr, nullptr, 1e-5f,
+                          fp32_plan ? y32.as<float>() : nullptr, fp32_plan ? nullptr : a_hi.as<bf16>(),
+                          (!fp32_plan && (plan & PLAN_SPLIT_HEADS)) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+        if (fp32_plan) IEF_CUDA(cudaMemcpyAsync(x32.p, y32.p, size_t(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
+      }
+      // heads (:125-128): one [M, D] x [2D, D]^T GEMM per modality, mu and logvar written to the user tensors
+      EpiParams eh;
+      eh.bias = heads[m].b; eh.out_f32 = mu_out[m] + row0 * D; eh.out_f32_b = lv_out[m] + row0 * D; eh.ld_f32 = D;
+      eh.split_col = D;
+      if (fp32_plan) {
+        IEF_TRY(gemm_simt(x32.as<float>(), D, heads[m].w, D, int(M), 2 * D, D, eh, stream));
+      } else {
+        GemmTcArgs gh;
+        gh.A_hi = a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>(); gh.W_hi = heads[m].w_hi; gh.W_lo = heads[m].w_lo;
+        gh.M = int(M); gh.N = 2 * D; gh.K = D; gh.lda = D; gh.ldw = D;
+        gh.nsplit = (plan & PLAN_SPLIT_HEADS) ? 3 : 1;
+        IEF_TRY(gemm_tc(gh, eh, num_sms, stream));
+      }
+    }
+    // uncertainty-weighted fusion (:130-144)
+    const bool rsp = !fp32_plan && (plan & PLAN_SPLIT_REFINE);
+    float* fused_out = fused + row0 * D;
+    float* xcur = (R == 0) ? fused_out : x32.as<float>();
+    IEF_TRY(fuse(image_mu + row0 * D, event_mu + row0 * D, image_logvar + row0 * D, event_logvar + row0 * D, M * D,
+                 factor, eps, w_i + row0 * D, w_e + row0 * D, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
+                 (rsp && R > 0) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+    // iterative refinement (:146-149): x <- x - lambda * (W2 relu(W1 x + b1) + b2)
+    for (int i = 0; i < R; ++i) {
+      const bool last = (i == R - 1);
+      float* xnext = last ? fused_out : x32.as<float>();
+      if (fp32_plan) {
+        EpiParams e1;
+        e1.bias = ref1[i].b; e1.act = ACT_RELU; e1.out_f32 = h32.as<float>(); e1.ld_f32 = D;
+        IEF_TRY(gemm_simt(x32.as<float>(), D, ref1[i].w, D, int(M), D, D, e1, stream));
+        EpiParams e2;
+        e2.bias = ref2[i].b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.alpha = -lambda_ref;
+        e2.out_f32 = xnext; e2.ld_f32 = D;
+        IEF_TRY(gemm_simt(h32.as<float>(), D, ref2[i].w, D, int(M), D, D, e2, stream));
+      } else {
+        EpiParams e1;
+        e1.bias = ref1[i].b; e1.act = ACT_RELU; e1.out_hi = h_hi.as<bf16>(); e1.out_lo = rsp ? h_lo.as<bf16>() : nullptr;
+        e1.ld_bf = D;
+        GemmTcArgs g1;
+        g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = ref1[i].w_hi; g1.W_lo = ref1[i].w_lo;
+        g1.M = int(M); g1.N = D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = rsp ? 3 : 1;
+        IEF_TRY(gemm_tc(g1, e1, num_sms, stream));
+        EpiParams e2;
+        e2.bias = ref2[i].b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.alpha = -lambda_ref;
+        e2.out_f32 = xnext; e2.ld_f32 = D;
+        if (!last) { e2.out_hi = a_hi.as<bf16>(); e2.out_lo = rsp ? a_lo.as<bf16>() : nullptr; e2.ld_bf = D; }
+        GemmTcArgs g2;
+        g2.A_hi = h_hi.as<bf16>(); g2.A_lo = h_lo.as<bf16>(); g2.W_hi = ref2[i].w_hi; g2.W_lo = ref2[i].w_lo;
+        g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D; g2.nsplit = rsp ? 3 : 1;
+        IEF_TRY(gemm_tc(g2, e2, num_sms, stream));
+      }
+    }
+    // classifier (:150) stays fp32 in every plan
+    IEF_TRY(classifier(fused_out, M, D, cls_w, cls_b, logits + row0, scores ? scores + row0 : nullptr, num_sms, stream));
+  }
+  return IEFVAD_OK;
+}
+
+void Model::destroy() {
+  DevBuf* all[] = {&params_f32, &params_hi, &params_lo, &x32, &y32, &a_hi, &a_lo, &h_hi, &h_lo,
+                   &qb, &kb, &vtb, &qkv32, &attn32, &h32};
+  for (DevBuf* b : all) b->release();
+}
+
+}  // namespace iefvad

@@ -1,0 +1,87 @@
+// Device-resident IEF-VAD model: fp32 master parameters (state_dict layout of model/imf_vad.py:69-107),
+// packed bf16 hi/lo copies for the tensor-core plans, and a grow-only activation workspace.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace iefvad {
+
+// precision plan: -1 = every contraction in fp32 FFMA; otherwise a bit mask of which bf16 GEMM groups use the
+// 3-term split (A_hi.W_hi + A_hi.W_lo + A_lo.W_hi)
+enum : int { PLAN_FP32 = -1, PLAN_SPLIT_ENCODER = 1, PLAN_SPLIT_HEADS = 2, PLAN_SPLIT_REFINE = 4 };
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need);   // grow-only; contents are NOT preserved
+  void release();
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Linear {          // y = x W^T + b, W [out, in]
+  float* w = nullptr;    // fp32 master
+  float* b = nullptr;
+  bf16* w_hi = nullptr;
+  bf16* w_lo = nullptr;
+  int out = 0, in = 0;
+};
+
+struct ParamSlot {
+  float* dst = nullptr;
+  long long numel = 0;
+  bf16* hi = nullptr;    // packed copies refreshed on upload (weights only)
+  bf16* lo = nullptr;
+  bool loaded = false;
+};
+
+struct Model {
+  int D = 0, H = 0, L = 0, R = 0, dh = 0, dhp = 0;
+  float lambda_ref = 0.5f, factor = 1.f, eps = 1e-8f;
+  int plan = PLAN_SPLIT_HEADS | PLAN_SPLIT_REFINE;
+  long long max_rows = 32768;    // rows per internal slab (whole batch elements)
+  int num_sms = 148;
+  int device = 0;
+
+  // parameters, index 0 = image, 1 = event
+  std::vector<Linear> in_proj[2], out_proj[2];
+  std::vector<float*> ln_w[2], ln_b[2];
+  float* whiten_w[2] = {nullptr, nullptr};
+  float* whiten_b[2] = {nullptr, nullptr};
+  Linear heads[2];               // rows [0, D) = mu, [D, 2D) = logvar
+  std::vector<Linear> ref1, ref2;
+  float* cls_w = nullptr;
+  float* cls_b = nullptr;
+
+  std::unordered_map<std::string, ParamSlot> slots;
+  DevBuf params_f32, params_hi, params_lo;
+
+  // workspace (one slab)
+  DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32;
+  long long ws_rows = 0;
+  int ws_T = 0;
+
+  int init(int embed_dim, int heads, int layers, int refine_steps, float lambda, int noise_model, float nu, float epsilon);
+  int set_param(const char* key, const float* dptr, long long numel, cudaStream_t stream);
+  int check_loaded() const;
+  int reserve_workspace(long long rows, int B, int T, bool fp32_plan);
+  int forward(const void* img, const void* ev, int in_dtype, long long B, long long T, float* fused, float* logits,
+              float* image_mu, float* event_mu, float* image_logvar, float* event_logvar, float* w_i, float* w_e,
+              float* scores, cudaStream_t stream);
+  void destroy();
+};
+
+// Multi-head self-attention block on a slab, shared with the model/module.py Transformer (D4):
+//   plan >= 0: a_hi (+a_lo) -> QKV tcgen05 GEMM -> attn_tc -> ctx_hi [M, D] bf16
+//   plan <  0: x32 -> fp32 GEMM -> attn_simt -> ctx32 [M, D] fp32
+struct MhaScratch {
+  bf16 *q, *k, *vt;          // TC plan operand layouts
+  float *qkv32;              // fp32 plan
+};
+
+}  // namespace iefvad

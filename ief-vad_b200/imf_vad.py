@@ -1,0 +1,185 @@
+"""Drop-in replacements for the reference's `model.imf_vad.MMFMIL` and `MultiModal_Fusion_Attn_Iter`
+(model/imf_vad.py:5-161) whose forward runs entirely in libiefvad.so on an sm_100a GPU.
+
+Same constructor signatures, attributes, `forward(img_visual, ev_visual, padding_mask, text, lengths,
+return_attn=False)` signature, output dict (8 fp32 tensors, model/imf_vad.py:152-161) and `state_dict()` keys /
+shapes, so `main.py`, `test.py`, `test2.py` and `train/*_test.py` of the reference can use it unchanged (see
+INTEGRATION.md for the one-line shim).  The nn.Module only *owns* the parameters (fp32 `nn.Parameter`s, created
+in the reference's order so `torch.manual_seed(s)` yields bit-identical initial weights); all arithmetic happens
+in hand-written CUDA kernels reached through the C ABI - there is no PyTorch or CPU fallback."""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_MODALITIES = ("image", "event")
+
+
+class MultiModal_Fusion_Attn_Iter(nn.Module):
+    """Parameter layout of model/imf_vad.py:69-107; forward of :109-161 on the GPU."""
+
+    def __init__(self, embed_dim, num_layers=2, num_heads=8, dropout=0.1, num_refinement_steps=3, lambda_ref=0.5,
+                 noise_model="StudentT", nu=5, epsilon=1e-8):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_layers = num_layers
+        self.num_heads = num_heads
+        self.num_refinement_steps = num_refinement_steps
+        self.lambda_ref = lambda_ref
+        self.noise_model = noise_model
+        self.nu = nu
+        self.epsilon = epsilon
+        self.dropout = dropout          # attention dropout only acts in train(); this path is forward-only (eval)
+        self.precision = os.environ.get("IEFVAD_PLAN", "B")
+
+        # nn.MultiheadAttention / LayerNorm / Linear instances are used purely as parameter containers: they give
+        # the reference's state_dict keys and consume the RNG exactly like the reference constructor does
+        # (attention stacks of both modalities first, then the four heads, the refinement MLPs, the classifier).
+        for mod in _MODALITIES:
+            setattr(self, f"{mod}_attn_layers", nn.ModuleList(
+                nn.MultiheadAttention(embed_dim, num_heads, dropout=dropout, batch_first=True)
+                for _ in range(num_layers)))
+            setattr(self, f"{mod}_norms", nn.ModuleList(nn.LayerNorm(embed_dim) for _ in range(num_layers)))
+        for mod in _MODALITIES:
+            setattr(self, f"whiten_{mod}", nn.LayerNorm(embed_dim))
+        for kind in ("mu", "logvar"):
+            for mod in _MODALITIES:
+                setattr(self, f"{mod}_{kind}", nn.Linear(embed_dim, embed_dim))
+        if num_refinement_steps == 0:
+            blocks = [nn.Identity()]
+        else:
+            blocks = [nn.Sequential(nn.Linear(embed_dim, embed_dim), nn.ReLU(), nn.Linear(embed_dim, embed_dim))
+                      for _ in range(num_refinement_steps)]
+        self.refinement_blocks = nn.ModuleList(blocks)
+        self.classifier = nn.Linear(embed_dim, 1)
+
+        self._handle: Optional[int] = None
+        self._handle_device: Optional[torch.device] = None
+        self._uploaded: Dict[str, tuple] = {}
+
+    # ------------------------------------------------------------------ native model management
+    def _release(self):
+        if getattr(self, "_handle", None):
+            _lib.lib.iefvad_model_destroy(self._handle)
+        self._handle = None
+        self._uploaded = {}
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _native(self, device: torch.device) -> int:
+        if self._handle is not None and self._handle_device == device:
+            return self._handle
+        self._release()
+        if self.noise_model not in _lib.NOISE:                       # model/imf_vad.py:137-138
+            raise ValueError("Unsupported noise_model. Choose 'Gaussian' or 'StudentT'.")
+        h = _lib._vp()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib.iefvad_model_create(
+                h, int(self.embed_dim), int(self.num_heads), int(self.num_layers), int(self.num_refinement_steps),
+                float(self.lambda_ref), _lib.NOISE[self.noise_model], float(self.nu), float(self.epsilon)))
+        self._handle, self._handle_device = h.value, device
+        return self._handle
+
+    def _sync_params(self, handle: int, device: torch.device, stream: int) -> None:
+        """Upload parameters whose storage or version changed since the last forward (load_state_dict,
+        optimizer steps, .to())."""
+        for name, p in self.named_parameters():
+            tag = (p.data_ptr(), p._version)
+            if self._uploaded.get(name) == tag:
+                continue
+            if p.device != device:
+                raise RuntimeError(f"parameter {name} is on {p.device} but the inputs are on {device}; "
+                                   "call model.to(device) first")
+            src = p.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            _lib.check(_lib.lib.iefvad_model_set_param(handle, ("temporal." + name).encode(), src.data_ptr(),
+                                                       src.numel(), stream))
+            self._uploaded[name] = tag
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, image_features: torch.Tensor, event_features: torch.Tensor,
+                with_scores: bool = False) -> Dict[str, torch.Tensor]:
+        if self.noise_model not in _lib.NOISE:
+            raise ValueError("Unsupported noise_model. Choose 'Gaussian' or 'StudentT'.")
+        if not (image_features.is_cuda and event_features.is_cuda):
+            raise RuntimeError("IEF-VAD B200 path is CUDA-only: inputs must live on an sm_100a device "
+                               "(there is no CPU fallback)")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "the B200 path implements the inference forward only (no autograd, no attention dropout); "
+                "call model.eval() and/or wrap the call in torch.no_grad()")
+        if image_features.dim() != 3 or image_features.shape != event_features.shape:
+            raise RuntimeError(f"expected two [B, T, {self.embed_dim}] tensors, got {tuple(image_features.shape)} "
+                               f"and {tuple(event_features.shape)}")
+        B, T, D = image_features.shape
+        if D != self.embed_dim:
+            raise RuntimeError(f"last dimension {D} != embed_dim {self.embed_dim}")
+        device = image_features.device
+        codes = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+        if image_features.dtype not in codes or event_features.dtype != image_features.dtype:
+            image_features, event_features = image_features.float(), event_features.float()
+        img = image_features.contiguous()
+        ev = event_features.contiguous()
+        plan = _lib.PLANS.get(str(self.precision))
+        if plan is None:
+            raise ValueError(f"unknown precision plan {self.precision!r}; choose from {sorted(_lib.PLANS)}")
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            h = self._native(device)
+            self._sync_params(h, device, stream)
+            _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
+            wide = torch.empty((7, B, T, D), dtype=torch.float32, device=device)
+            logits = torch.empty((B, T, 1), dtype=torch.float32, device=device)
+            scores = torch.empty((B, T), dtype=torch.float32, device=device) if with_scores else None
+            _lib.check(_lib.lib.iefvad_model_forward(
+                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], B, T,
+                wide[0].data_ptr(), logits.data_ptr(), wide[1].data_ptr(), wide[2].data_ptr(), wide[3].data_ptr(),
+                wide[4].data_ptr(), wide[5].data_ptr(), wide[6].data_ptr(), _lib.ptr(scores), stream))
+        out = {
+            "fused": wide[0], "logits": logits, "image_mu": wide[1], "event_mu": wide[2],
+            "image_logvar": wide[3], "event_logvar": wide[4], "w_i": wide[5], "w_e": wide[6],
+        }
+        if with_scores:
+            out["scores"] = scores
+        return out
+
+
+class MMFMIL(nn.Module):
+    """model/imf_vad.py:5-44: holds the bookkeeping attributes and forwards to `self.temporal`."""
+
+    def __init__(self, num_class: int, embed_dim: int, visual_length: int, visual_width: int, visual_head: int,
+                 visual_layers: int, attn_window: int, prompt_prefix: int, prompt_postfix: int, device, args):
+        super().__init__()
+        self.num_class = num_class
+        self.visual_length = visual_length
+        self.visual_width = visual_width
+        self.embed_dim = embed_dim
+        self.attn_window = attn_window
+        self.prompt_prefix = prompt_prefix
+        self.prompt_postfix = prompt_postfix
+        self.device = device
+        # like the reference (:30-38) the positional visual_head / visual_layers are ignored in favour of args.*
+        self.temporal = MultiModal_Fusion_Attn_Iter(
+            embed_dim,
+            num_layers=args.visual_layers,
+            num_heads=args.visual_head,
+            num_refinement_steps=args.num_refinement_steps,
+            lambda_ref=args.lambda_ref,
+            noise_model=args.noise_model,
+            nu=args.nu,
+        )
+
+    def forward(self, img_visual, ev_visual, padding_mask=None, text=None, lengths=None, return_attn=False):
+        # padding_mask / text / lengths / return_attn are accepted and ignored, exactly as at :40-44;
+        # the fp16/bf16 -> fp32 cast of :41-42 happens inside the ingest kernel.
+        return self.temporal(img_visual, ev_visual)

@@ -1,0 +1,100 @@
+"""torch-tensor wrappers over the stand-alone operators of libiefvad.so (include/iefvad.h).
+
+Every function takes CUDA tensors, allocates its outputs with torch and launches on the current stream.
+There is no CPU implementation: a non-CUDA tensor raises."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+PLAN_CODES = {"fp32": -1, "bf16": 0, "split": 1}
+ACTS = {None: 0, "none": 0, "relu": 1, "quickgelu": 2}
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: CUDA tensor required (the B200 path has no CPU fallback), got {t.device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def fuse(mu_i, mu_e, logvar_i, logvar_e, noise_model: str = "StudentT", nu: float = 8, epsilon: float = 1e-8
+         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """model/imf_vad.py:130-144 -> (w_i, w_e, fused)."""
+    if noise_model == "Gaussian":
+        factor = 1.0
+    elif noise_model == "StudentT":
+        factor = (nu + 1) / nu
+    else:
+        raise ValueError("Unsupported noise_model. Choose 'Gaussian' or 'StudentT'.")
+    a, b, c, d = (_f32c(t, "fuse") for t in (mu_i, mu_e, logvar_i, logvar_e))
+    w_i, w_e, fused = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib.iefvad_fuse(a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), a.numel(), factor,
+                                        epsilon, w_i.data_ptr(), w_e.data_ptr(), fused.data_ptr(), _stream(a)))
+    return w_i, w_e, fused
+
+
+def layernorm(x, w1, b1, w2=None, b2=None, eps: float = 1e-5) -> torch.Tensor:
+    x = _f32c(x, "layernorm")
+    D = x.shape[-1]
+    out = torch.empty_like(x)
+    ws = [_f32c(t, "layernorm") if t is not None else None for t in (w1, b1, w2, b2)]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_layernorm(x.data_ptr(), x.numel() // D, D, *[_lib.ptr(t) for t in ws], eps,
+                                             out.data_ptr(), _stream(x)))
+    return out
+
+
+def linear(x, w, bias=None, resid=None, alpha: float = 1.0, act: Optional[str] = None, plan: str = "bf16",
+           tile_n: int = 0) -> torch.Tensor:
+    """out = (resid or 0) + alpha * act(x @ w.T + bias)."""
+    x = _f32c(x, "linear")
+    w = _f32c(w, "linear")
+    in_f, out_f = x.shape[-1], w.shape[0]
+    rows = x.numel() // in_f
+    out = torch.empty(x.shape[:-1] + (out_f,), dtype=torch.float32, device=x.device)
+    bias = _f32c(bias, "linear") if bias is not None else None
+    resid = _f32c(resid, "linear") if resid is not None else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_linear(x.data_ptr(), w.data_ptr(), _lib.ptr(bias), _lib.ptr(resid), alpha,
+                                          ACTS[act], rows, in_f, out_f, PLAN_CODES[plan], tile_n, out.data_ptr(),
+                                          _stream(x)))
+    return out
+
+
+def mha(x, in_w, in_b, out_w, out_b, num_heads: int, attn_mask=None, key_padding_mask=None, plan: str = "bf16"
+        ) -> torch.Tensor:
+    """nn.MultiheadAttention(batch_first=True)(x, x, x)[0], eval mode.  x [B, T, D]."""
+    x = _f32c(x, "mha")
+    B, T, D = x.shape
+    out = torch.empty_like(x)
+    in_w, in_b, out_w, out_b = (_f32c(t, "mha") for t in (in_w, in_b, out_w, out_b))
+    am = _f32c(attn_mask, "mha") if attn_mask is not None else None
+    kp = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_mha(x.data_ptr(), in_w.data_ptr(), in_b.data_ptr(), out_w.data_ptr(),
+                                       out_b.data_ptr(), B, T, D, num_heads, _lib.ptr(am), _lib.ptr(kp),
+                                       PLAN_CODES[plan], out.data_ptr(), _stream(x)))
+    return out
+
+
+def classifier(x, w, bias, with_scores: bool = False):
+    x = _f32c(x, "classifier")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    logits = torch.empty(x.shape[:-1] + (1,), dtype=torch.float32, device=x.device)
+    scores = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device) if with_scores else None
+    w, bias = _f32c(w, "classifier"), _f32c(bias, "classifier")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_classifier(x.data_ptr(), rows, D, w.data_ptr(), bias.data_ptr(), logits.data_ptr(),
+                                              _lib.ptr(scores), _stream(x)))
+    return (logits, scores) if with_scores else logits

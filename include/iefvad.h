@@ -1,0 +1,119 @@
+/* libiefvad - C ABI of the B200-native IEF-VAD inference hot path.
+ *
+ * The reference (EavnJeong/IEF-VAD) has no FFI / plugin boundary: its hot path is the Python nn.Module
+ * surface `model.imf_vad.MMFMIL` plus `train.loss.CLAS2` and scikit-learn's AUC / AP.  This header is the
+ * boundary a binding for that path would target; every entry point cites the reference interface it
+ * replaces.  The Python host side in `ief-vad_b200/` (ctypes) mirrors the reference's module API on top of it.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only.  Unless a parameter says "host", every data pointer is a DEVICE
+ *     pointer on the current CUDA device; `stream` is a cudaStream_t passed as void* (NULL = legacy default).
+ *   - every function returns 0 on success; otherwise a non-zero code (1 invalid argument, 2 CUDA error,
+ *     3 bad state) and `iefvad_last_error()` holds a message (thread-local).
+ *   - nothing synchronises the host unless stated; inputs are never modified.
+ *   - there is NO CPU implementation behind this ABI: without an sm_100a device every compute call fails.
+ */
+#ifndef IEFVAD_H_
+#define IEFVAD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IEFVAD_ABI_VERSION 1
+
+/* input element types (`in_dtype`) */
+#define IEFVAD_F32 0
+#define IEFVAD_F16 1
+#define IEFVAD_BF16 2
+
+/* noise models, model/imf_vad.py:130-138 */
+#define IEFVAD_NOISE_GAUSSIAN 0
+#define IEFVAD_NOISE_STUDENT_T 1
+
+/* precision plans (`plan`): -1 = every contraction in fp32 FFMA (1e-5 class);
+ * >= 0 = tcgen05 bf16 GEMMs, OR-mask of the GEMM groups that use the 3-term bf16 split */
+#define IEFVAD_PLAN_FP32 (-1)
+#define IEFVAD_PLAN_BF16 0
+#define IEFVAD_PLAN_SPLIT_ENCODER 1
+#define IEFVAD_PLAN_SPLIT_HEADS 2
+#define IEFVAD_PLAN_SPLIT_REFINE 4
+#define IEFVAD_PLAN_A (IEFVAD_PLAN_SPLIT_HEADS)
+#define IEFVAD_PLAN_B (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_SPLIT_REFINE) /* default */
+
+int iefvad_abi_version(void);
+const char* iefvad_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model object - replaces MMFMIL / MultiModal_Fusion_Attn_Iter construction, model/imf_vad.py:6-38, :48-107
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct iefvad_model iefvad_model;
+
+/* embed_dim: multiple of 128 in [128, 1024]; embed_dim / num_heads in {32, 64, 96, 128}.
+ * noise_model other than the two constants fails with the reference's message (model/imf_vad.py:138). */
+int iefvad_model_create(iefvad_model** out, int embed_dim, int num_heads, int num_layers, int num_refinement_steps,
+                        float lambda_ref, int noise_model, float nu, float epsilon);
+void iefvad_model_destroy(iefvad_model* m);
+
+/* Upload one parameter by its reference state_dict key (e.g. "temporal.image_attn_layers.0.in_proj_weight",
+ * "temporal.refinement_blocks.3.2.bias"; the 78 tensors of model/imf_vad.py:69-107).  `data`: device fp32,
+ * contiguous, `numel` elements.  bf16 hi/lo copies are refreshed on the given stream. */
+int iefvad_model_set_param(iefvad_model* m, const char* key, const float* data, int64_t numel, void* stream);
+
+int iefvad_model_set_plan(iefvad_model* m, int plan);
+int iefvad_model_get_plan(const iefvad_model* m);
+/* rows per internal slab (bounds the activation workspace); default 32768 */
+int iefvad_model_set_max_rows(iefvad_model* m, int64_t max_rows);
+
+/* Replaces MMFMIL.forward(img_visual, ev_visual, padding_mask, text, lengths), model/imf_vad.py:40-44 ->
+ * :109-161.  padding_mask / text / lengths are ignored by the reference and have no parameter here.
+ * img, ev: [B, T, embed_dim] contiguous, element type `in_dtype`.  Outputs (fp32, contiguous):
+ * fused, image_mu, event_mu, image_logvar, event_logvar, w_i, w_e: [B, T, embed_dim]; logits: [B, T, 1];
+ * scores (optional, may be NULL): sigmoid(logits) [B, T] (train/ucf_test.py:114). */
+int iefvad_model_forward(iefvad_model* m, const void* img, const void* ev, int in_dtype, int64_t B, int64_t T,
+                         float* fused, float* logits, float* image_mu, float* event_mu, float* image_logvar,
+                         float* event_logvar, float* w_i, float* w_e, float* scores, void* stream);
+
+/* Same path with HOST buffers: copies img / ev host->device, runs the forward, copies logits (and, when
+ * non-NULL, scores) device->host and synchronises the stream.  The seven wide outputs stay on the device in
+ * caller-provided DEVICE buffers (pass NULL to let the library keep them in scratch).  Host pointers should be
+ * pinned for full copy bandwidth.  This is the call `bench.py` times for `e2e`. */
+int iefvad_model_forward_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
+                              int64_t T, float* logits_host, float* scores_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone operators (device pointers) - the same kernels the forward uses, exposed for parity tests
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Uncertainty-weighted fusion, model/imf_vad.py:130-144.  n = number of elements (multiple of 4).
+ * factor = 1 (Gaussian) or (nu+1)/nu (StudentT).  fused may be NULL. */
+int iefvad_fuse(const float* mu_i, const float* mu_e, const float* logvar_i, const float* logvar_e, int64_t n,
+                float factor, float epsilon, float* w_i, float* w_e, float* fused, void* stream);
+
+/* nn.LayerNorm (eps 1e-5) applied once, or twice when w2/b2 are non-NULL (model/imf_vad.py:116-117). */
+int iefvad_layernorm(const float* x, int64_t rows, int dim, const float* w1, const float* b1, const float* w2,
+                     const float* b2, float eps, float* out, void* stream);
+
+/* nn.Linear with fused epilogue: out = (resid ? resid : 0) + alpha * act(x W^T + bias); act: 0 none, 1 ReLU,
+ * 2 QuickGELU (model/module.py:15-17).  x [rows, in_f] fp32, w [out_f, in_f] fp32, out [rows, out_f] fp32.
+ * plan: -1 fp32 FFMA, 0 bf16 tcgen05, 1 split-bf16 tcgen05.  tile_n: 0 = heuristic, or 64 / 128 / 256. */
+int iefvad_linear(const float* x, const float* w, const float* bias, const float* resid, float alpha, int act,
+                  int64_t rows, int in_f, int out_f, int plan, int tile_n, float* out, void* stream);
+
+/* nn.MultiheadAttention(batch_first=True)(x, x, x)[0] in eval mode (model/imf_vad.py:115; torch/nn/functional.py:6244).
+ * x [B, T, D] fp32; in_w [3D, D], in_b [3D], out_w [D, D], out_b [D].  attn_mask: optional additive [T, T] fp32;
+ * key_padding_mask: optional [B, T] uint8 (non-zero = ignore).  plan as for iefvad_linear. */
+int iefvad_mha(const float* x, const float* in_w, const float* in_b, const float* out_w, const float* out_b,
+               int64_t B, int64_t T, int D, int num_heads, const float* attn_mask, const uint8_t* key_padding_mask,
+               int plan, float* out, void* stream);
+
+/* Linear(embed_dim -> 1), model/imf_vad.py:150 (+ optional sigmoid). */
+int iefvad_classifier(const float* x, int64_t rows, int dim, const float* w, const float* bias, float* logits,
+                      float* scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IEFVAD_H_ */

@@ -1,0 +1,281 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference
+(/root/reference, read-only) and scikit-learn in the authoring container.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, so its outputs are committed here as small .npz files and are
+what `oracle/iefvad_oracle.py` (and, through it and directly, the CUDA path) is pinned against.  Weights and
+inputs of the full-size cases are regenerated from seeds by `ief-vad_b200/synth.py`; the fixtures store a sha256 of
+the state_dict so a seed/RNG drift is detected instead of silently comparing different models."""
+import os
+import sys
+import types
+
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("IEFVAD_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# stubs for packages the reference's eval loop imports but that are not installed / not wanted
+for name in ("matplotlib", "matplotlib.pyplot", "wandb"):
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.log = lambda *a, **k: None
+        m.init = lambda *a, **k: None
+        sys.modules[name] = m
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+
+from model.imf_vad import MMFMIL as RefMMFMIL  # noqa: E402  (reference)
+from model import layers as ref_layers  # noqa: E402
+from model import module as ref_module  # noqa: E402
+from train.loss import CLAS2 as ref_CLAS2  # noqa: E402
+from train import ucf_test as ref_ucf_test  # noqa: E402
+from sklearn.metrics import average_precision_score, roc_auc_score  # noqa: E402
+
+import importlib.util  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("synth", os.path.join(ROOT, "ief-vad_b200", "synth.py"))
+synth = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(synth)
+
+torch.set_num_threads(8)
+OUT_KEYS = ["fused", "logits", "image_mu", "event_mu", "image_logvar", "event_logvar", "w_i", "w_e"]
+
+
+def sd_np(model):
+    return {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def small_models():
+    """Tiny models with every tensor stored: weights, inputs, all 8 outputs."""
+    cases = [
+        ("small_studentt", dict(noise_model="StudentT", nu=8, num_refinement_steps=3, visual_head=4), 128, 2, 24),
+        ("small_gaussian", dict(noise_model="Gaussian", nu=8, num_refinement_steps=2, visual_head=2), 128, 3, 17),
+        ("small_r0", dict(noise_model="StudentT", nu=5, num_refinement_steps=0, visual_head=4, lambda_ref=0.25),
+         128, 1, 40),
+    ]
+    for name, over, D, B, T in cases:
+        args = synth.default_args(**over)
+        model = synth.build_model(RefMMFMIL, seed=7, embed_dim=D, args=args).eval()
+        synth.perturb_(model, seed=11, scale=0.2)
+        g = torch.Generator("cpu").manual_seed(5)
+        img = torch.randn(B, T, D, generator=g)
+        ev = torch.randn(B, T, D, generator=g)
+        with torch.no_grad():
+            out = model(img, ev, None, None, None)
+        arrays = {"param:" + k: v for k, v in sd_np(model).items()}
+        arrays.update({"out:" + k: out[k].numpy() for k in OUT_KEYS})
+        arrays.update(img=img.numpy(), ev=ev.numpy(), heads=np.int64(args.visual_head), nu=np.float64(args.nu),
+                      lambda_ref=np.float64(args.lambda_ref), noise_model=np.array(args.noise_model))
+        save(name + ".npz", **arrays)
+
+
+def full_models():
+    """Full-size (768-d, 2 layers, 8 heads, 10 refinement steps) model at the default seed: logits + row samples of
+    the wide tensors + digests.  Weights/inputs come from synth (seed 0 / video seeds)."""
+    rows = np.array([0, 1, 37, 100, 255])
+    for tag, perturbed in (("full_default", False), ("full_perturbed", True)):
+        model = synth.build_model(RefMMFMIL, seed=0).eval()
+        if perturbed:
+            synth.perturb_(model, seed=1, scale=0.1)
+        digest = synth.state_digest(model.state_dict())
+        arrays = {"digest": np.array(digest)}
+        # C1: B=1, T=256 (fp16 storage like the .npy embeddings)
+        img, ev = synth.make_video(0, 256)
+        with torch.no_grad():
+            out = model(img[None], ev[None], None, None, None)
+        arrays["c1:logits"] = out["logits"].numpy().reshape(-1)
+        for k in OUT_KEYS:
+            if k != "logits":
+                arrays[f"c1:{k}:rows"] = out[k].numpy()[0, rows]
+        arrays["c1:rows"] = rows
+        # ragged direct call: B=3, T=40 (T not a multiple of the 128-row tiles, 3 batch elements in one tile)
+        vids = [synth.make_video(10 + i, 40) for i in range(3)]
+        img3 = torch.stack([v[0] for v in vids])
+        ev3 = torch.stack([v[1] for v in vids])
+        with torch.no_grad():
+            out = model(img3, ev3, None, None, None)
+        arrays["b3t40:logits"] = out["logits"].numpy().reshape(3, 40)
+        for k in OUT_KEYS:
+            if k != "logits":
+                arrays[f"b3t40:{k}:row7"] = out[k].numpy()[:, 7]
+        # a chunked video: T=700 -> 3 chunks of 256 (data/tools.py:100-114), fp32 logits of the 700 valid rows
+        img7, ev7 = synth.make_video(20, 700)
+        ci, ce = synth.chunk_video(img7), synth.chunk_video(ev7)
+        with torch.no_grad():
+            out = model(ci, ce, None, None, None)
+        arrays["t700:logits"] = out["logits"].numpy().reshape(-1)[:700]
+        # direct long call T=1000 (multi key-block streaming softmax, ragged tail)
+        img1k, ev1k = synth.make_video(21, 1000)
+        with torch.no_grad():
+            out = model(img1k[None], ev1k[None], None, None, None)
+        arrays["t1000:logits"] = out["logits"].numpy().reshape(-1)
+        save(tag + ".npz", **arrays)
+
+
+def clas2_cases():
+    g = torch.Generator("cpu").manual_seed(3)
+    B, T = 16, 256
+    logits = 2.0 * torch.randn(B, T, 1, generator=g)
+    # force ties and extreme values
+    logits[0, :40] = 0.5
+    logits[1, 3] = 30.0
+    logits[2] = -30.0
+    lengths = torch.tensor([256, 255, 17, 16, 15, 1, 100, 200, 32, 31, 33, 64, 128, 250, 2, 240])
+    labels = torch.zeros(B, 14)
+    labels[::2, 0] = 1.0
+    labels[1::2, 3] = 1.0
+    loss = ref_CLAS2(logits, labels, lengths, "cpu")
+    save("clas2.npz", logits=logits.numpy(), lengths=lengths.numpy(), labels=labels.numpy(), loss=loss.numpy())
+
+
+def eval_loop_case():
+    """The reference's own train/ucf_test.py:test() on a synthetic loader: 30 UCF-style videos, full-size
+    default-seed model, CPU."""
+    n = 30
+    rng = np.random.default_rng(9)
+    T = np.clip(np.round(np.exp(rng.normal(np.log(120.0), 0.9, n))), 1, 900).astype(np.int64)
+    T[:6] = [1, 16, 255, 256, 257, 512]
+    classes = synth.config_classes("ucf", n)
+    gt = synth.make_gt(T, classes)
+    model = synth.build_model(RefMMFMIL, seed=0).eval()
+
+    class Loader:
+        def __iter__(self):
+            for v in range(n):
+                img, ev = synth.make_video(100 + v, int(T[v]))
+                # what data/dataset.py:34-52 + DataLoader(batch_size=1) deliver
+                from data.tools import process_split
+                fi, ln = process_split(img.numpy(), 256)
+                fe, _ = process_split(ev.numpy(), 256)
+                yield (torch.from_numpy(fi)[None], torch.from_numpy(fe)[None], [classes[v]], torch.tensor([ln]))
+
+    args = types.SimpleNamespace(exp_name="golden", dataset="ucfcrime")
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        captured = {}
+        real_auc = ref_ucf_test.roc_auc_score
+
+        def spy(gt_, pred):
+            captured.setdefault("first", np.asarray(pred)[::16].copy())
+            return real_auc(gt_, pred)
+
+        ref_ucf_test.roc_auc_score = spy
+        ret = ref_ucf_test.test(args, model, Loader(), 256, None, gt, "cpu")
+        ref_ucf_test.roc_auc_score = real_auc
+    finally:
+        os.chdir(cwd)
+    scores = captured["first"]
+    rep = np.repeat(scores, 16)
+    auc, ap = roc_auc_score(gt, rep), average_precision_score(gt, rep)
+    print("reference test() returned", ret, "recomputed", auc, ap)
+    save("eval_loop.npz", lengths=T, classes=np.array(classes), scores=scores.astype(np.float32), AUC=np.float64(auc),
+         AP=np.float64(ap), ret=np.array([float(x) for x in ret]) if ret is not None else np.zeros(0))
+
+
+def sklearn_cases():
+    rng = np.random.default_rng(12)
+    arrays = {}
+    for i, (n, tie, posr) in enumerate([(1000, 0.0, 0.3), (5000, 0.4, 0.05), (64, 0.9, 0.5), (3, 0.0, 0.5),
+                                        (2000, 0.2, 1.0), (2000, 0.2, 0.0)]):
+        s = rng.random(n).astype(np.float32)
+        if tie > 0:
+            s = np.round(s * (1.0 / tie)) * tie
+            s = s.astype(np.float32)
+        pos = (rng.random(n) < posr)
+        cnt = np.where(pos, rng.integers(1, 17, n), 0).astype(np.int64)     # positives among the 16 frames
+        gt = np.zeros((n, 16))
+        for j in range(n):
+            gt[j, :cnt[j]] = 1
+        gt = gt.reshape(-1)
+        rep = np.repeat(s.astype(np.float64), 16)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                auc = roc_auc_score(gt, rep)
+            except ValueError:
+                auc = float("nan")
+            ap = average_precision_score(gt, rep)
+        arrays[f"{i}:scores"] = s
+        arrays[f"{i}:pos"] = cnt
+        arrays[f"{i}:auc"] = np.float64(auc)
+        arrays[f"{i}:ap"] = np.float64(ap)
+    arrays["n"] = np.int64(6)
+    save("sklearn_auc.npz", **arrays)
+
+
+def layer_cases():
+    torch.manual_seed(21)
+    arrays = {}
+    B, T, Din, Dout = 2, 50, 128, 128
+    x = torch.randn(B, T, Din)
+    sim = ref_layers.SimilarityAdj(Din, Dout)
+    with torch.no_grad():
+        arrays["sim:w0"] = sim.weight0.numpy().copy()
+        arrays["sim:x"] = x.numpy()
+        arrays["sim:out_none"] = sim(x, None).numpy()
+        arrays["sim:out_len"] = sim(x, [50, 31]).numpy()
+        arrays["sim:seq_len"] = np.array([50, 31])
+        gc = ref_layers.GraphConvolution(Din, Dout, bias=True, residual=True)
+        adj = torch.softmax(torch.randn(B, T, T), dim=-1)
+        arrays["gc:w"] = gc.weight.numpy().copy()
+        arrays["gc:b"] = gc.bias.numpy().copy()
+        arrays["gc:adj"] = adj.numpy()
+        arrays["gc:out"] = gc(x, adj).numpy()
+        gc2 = ref_layers.GraphConvolution(Din, 256, bias=False, residual=True)
+        arrays["gc2:w"] = gc2.weight.numpy().copy()
+        arrays["gc2:conv_w"] = gc2.residual.weight.numpy().copy()
+        arrays["gc2:conv_b"] = gc2.residual.bias.numpy().copy()
+        arrays["gc2:out"] = gc2(x, adj).numpy()
+        # Transformer (seq-first), 2 layers, with key padding mask and additive attn mask
+        W, Hh, Lyr, Lseq, N = 128, 4, 2, 40, 3
+        mask = torch.zeros(Lseq, Lseq)
+        mask[torch.triu(torch.ones(Lseq, Lseq), diagonal=9) > 0] = -1e4
+        tr = ref_module.Transformer(W, Lyr, Hh, attn_mask=mask).eval()
+        synth.perturb_(tr, seed=4, scale=0.2)
+        xt = torch.randn(Lseq, N, W)
+        pad = torch.zeros(N, Lseq, dtype=torch.bool)
+        pad[1, 30:] = True
+        pad[2, 5:] = True
+        out_masked, _ = tr((xt, pad))
+        out_plain, _ = tr((xt, None))
+        for k, v in tr.state_dict().items():
+            arrays["tr:param:" + k] = v.numpy().copy()
+        arrays["tr:x"] = xt.numpy()
+        arrays["tr:pad"] = pad.numpy()
+        arrays["tr:mask"] = mask.numpy()
+        arrays["tr:out_masked"] = out_masked.numpy()
+        arrays["tr:out_nopad"] = out_plain.numpy()
+        arrays["tr:heads"] = np.int64(Hh)
+    save("layers.npz", **arrays)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["small", "full", "clas2", "eval", "sklearn", "layers"]
+    with torch.no_grad():
+        if "small" in which:
+            small_models()
+        if "full" in which:
+            full_models()
+        if "clas2" in which:
+            clas2_cases()
+        if "eval" in which:
+            eval_loop_case()
+        if "sklearn" in which:
+            sklearn_cases()
+        if "layers" in which:
+            layer_cases()
