@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the IEF-VAD inference hot path (BASELINE.json metric: fused frames/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ucf|xd|c1|c4|c5]
+
+A *step* is one pass of the hot path over one batch of synthetic input: for the default workload ("ucf", BASELINE
+configs[1]: 290 synthetic UCF-Crime-shaped videos, T_v <= 4096, 768-d fp16 image + event embeddings) that is the
+forward over every 256-row chunk of every video, score compaction, the score gather and frame-level AUC / AP
+(overall, Ano-AUC, class-wise).  N > 1 (torchrun, one rank per GPU): every rank evaluates its own 290-video set
+(weak scaling, no data-path collective) and one all_gather of the scores feeds the global AUC.
+
+value   = valid frames (embedding rows sum T_v over all ranks) / device time, inputs resident in HBM.
+e2e     = the same through the same public call with pinned HOST inputs (H2D inside the timed region, metrics D2H).
+roofline= the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of its launches, vs the measured
+          sustained bf16 peak of MEASURED_PEAKS.json.
+cpu_baseline / --impl reference = the oracle's torch-CPU port (the reference's arithmetic on the reference's own CPU
+          kernels; the Python reference itself cannot travel to the GPU box) on a bounded sample of the workload."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FLOPS_PER_FRAME_T256 = 47_187_456 + 12_288 * 256          # SURVEY.md 8d, algorithmic
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p.update(json.load(fh))
+            p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def build_workload(name: str, rank: int, world: int, synth):
+    """-> dict(lengths, classes, gt, video_ids) for the WHOLE job (all ranks), deterministic."""
+    if name in ("ucf", "xd"):
+        base = synth.config_lengths(name)
+        n = len(base)
+        lengths = np.concatenate([base for _ in range(world)])            # weak scaling: one set per rank
+        classes = synth.config_classes(name, n) * world
+        vids = np.arange(n * world)
+    elif name == "c1":
+        lengths, classes, vids = np.array([255] * world), ["Abuse"] * world, np.arange(world)
+    else:
+        raise ValueError(name)
+    return dict(lengths=lengths, classes=classes, gt=synth.make_gt(lengths, classes), video_ids=vids)
+
+
+def make_features(ev_obj, video_ids, lengths, synth, D):
+    feats_i, feats_e = [], []
+    for v in ev_obj.mine:
+        a, b = synth.make_video(int(video_ids[v]), int(lengths[v]), D)
+        feats_i.append(a)
+        feats_e.append(b)
+    return ev_obj.chunk_features(feats_i), ev_obj.chunk_features(feats_e)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_port_run(workload, sample_videos: int, steps: int, warmup: int, synth):
+    """Time the oracle's torch-CPU port on the first `sample_videos` videos with every host thread."""
+    from oracle import torch_port
+    from iefvad_b200.imf_vad import MMFMIL
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = synth.build_model(MMFMIL, seed=0)
+    P = {k: v.detach() for k, v in model.state_dict().items()}
+    lengths = workload["lengths"][:sample_videos]
+    vids = [synth.make_video(int(workload["video_ids"][v]), int(lengths[v])) for v in range(len(lengths))]
+    chunks = [(synth.chunk_video(a), synth.chunk_video(b)) for a, b in vids]
+    frames = int(lengths.sum())
+
+    def one_pass():
+        scores = []
+        with torch.no_grad():
+            for (ci, ce), T in zip(chunks, lengths):                       # per-video loop like train/ucf_test.py:70
+                out = torch_port.forward(P, ci, ce)
+                scores.append(torch.sigmoid(out["logits"].reshape(-1)[:int(T)]))
+        return torch.cat(scores)
+
+    for _ in range(warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / steps
+    return frames / dt, dt * 1e3, cores, f"first {len(lengths)} videos of the workload ({frames} frames), per-video loop"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ucf", choices=["ucf", "xd", "c1"])
+    ap.add_argument("--plan", default=None, help="precision plan override: B (default), A, bf16, split, fp32")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="videos in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from iefvad_b200 import synth
+
+    workload_names = {"ucf": "UCF-Crime test-split shape: 290 synthetic videos, T_v<=4096, 768-d fp16 image+event, "
+                             "chunked to 256 rows (data/tools.py:100-114)",
+                      "xd": "XD-Violence test-split shape: 800 synthetic videos", "c1": "B=1, T=256"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = build_workload(args.workload, 0, 1, synth)
+        # sized so K + W passes end within a few minutes on a server CPU (~10 k frames/s)
+        val, ms, cores, sample = cpu_port_run(wl, args.cpu_sample, max(1, args.steps), max(0, args.warmup), synth)
+        line = {"impl": "reference", "metric": "fused frames/sec (IEF-VAD inference)", "value": val, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_names[args.workload]},
+                "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from iefvad_b200 import _lib
+    from iefvad_b200.evaluate import Evaluator
+    from iefvad_b200.imf_vad import MMFMIL
+
+    model = synth.build_model(MMFMIL, seed=0).to(dev).eval()
+    if args.plan:
+        model.temporal.precision = args.plan
+    wl = build_workload(args.workload, rank, world, synth)
+    evaluator = Evaluator(model, wl["lengths"], wl["classes"], wl["gt"], rank=rank, world=world, device=dev)
+    img_c, ev_c = make_features(evaluator, wl["video_ids"], wl["lengths"], synth, model.embed_dim)
+    frames_total = int(wl["lengths"].sum())
+    rows_local = evaluator.local_chunks * evaluator.maxlen
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host_inputs: bool, steps: int):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = None
+        for _ in range(steps):
+            res = evaluator.step(host_inputs=host_inputs)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, res
+
+    with torch.no_grad():
+        # ---- device-resident run (value)
+        evaluator.set_device_features(img_c, ev_c)
+        for _ in range(max(3, args.warmup)):
+            evaluator.step()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = _lib.lib.iefvad_launch_count()
+        ms_dev, res = timed(False, args.steps)
+        launches = _lib.lib.iefvad_launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- end-to-end run (pinned host inputs, H2D inside the timed region)
+        evaluator.set_host_features(img_c, ev_c)
+        for _ in range(2):
+            evaluator.step(host_inputs=True)
+        ms_e2e, _ = timed(True, max(2, args.steps // 2))
+        # ---- per-kernel-class profile of one step (CUDA events around every launch of the forward)
+        evaluator.set_device_features(img_c, ev_c)
+        import ctypes as C
+        _lib.lib.iefvad_profile_enable(1)
+        evaluator.step(with_metrics=False)
+        torch.cuda.synchronize()
+        ms_k, work_k, n_k = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_int64 * 8)()
+        _lib.check(_lib.lib.iefvad_profile_read(ms_k, work_k, n_k))
+        _lib.lib.iefvad_profile_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    names = ["gemm_tc", "attn_tc", "layernorm", "fuse", "classifier", "ingest", "gemm_simt", "attn_simt"]
+    kernels = {}
+    for i, nm in enumerate(names):
+        if n_k[i]:
+            rate = work_k[i] / (ms_k[i] * 1e-3)
+            kernels[nm] = {"launches": int(n_k[i]), "ms": round(ms_k[i], 4),
+                           ("tflops" if i in (0, 1, 6, 7) else "gbs"): round(rate / (1e12 if i in (0, 1, 6, 7) else 1e9), 2)}
+    gemm_tflops = work_k[0] / (ms_k[0] * 1e-3) / 1e12 if n_k[0] else 0.0
+    peak_tf = float(pk["bf16_tflops_sustained"])
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16, fp32 accumulate)",
+                "achieved": round(gemm_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(gemm_tflops / peak_tf, 4), "traffic": None,
+                "peak_source": f"{pk['source']} sustained bf16 (MEASURED_PEAKS.json)",
+                "note": "algorithmic FLOPs (2MNK per launch; the 3-term bf16 split's extra MMAs are not counted) / "
+                        "sum of CUDA-event durations of the GEMM launches of one step",
+                "share_of_step": round(ms_k[0] / max(sum(ms_k), 1e-9), 4)}
+
+    value = frames_total / (ms_dev * 1e-3)
+    e2e_val = frames_total / (ms_e2e * 1e-3)
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, ms, cores, sample = cpu_port_run(build_workload(args.workload, 0, 1, synth), args.cpu_sample, 1, 1, synth)
+        cpu = {"value": round(v, 1), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+    line = {
+        "metric": "fused frames/sec (IEF-VAD inference)", "value": round(value, 1), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_dev, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_names[args.workload] + (f" x {world} ranks (one set per rank)" if world > 1 else ""),
+                   "videos": int(len(wl["lengths"])), "valid_frames": frames_total,
+                   "rows_incl_pad_per_rank": rows_local, "precision_plan": model.temporal.precision,
+                   "l2": "inputs larger than L2 (fp16 chunks %.0f MB per rank)" % (2 * img_c.numel() * 2 / 1e6),
+                   "parallelism": f"video-sharded x{world}, one all_gather of scores"},
+        "e2e": {"value": round(e2e_val, 1), "unit": "frames/s", "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": evaluator.h2d_bytes(), "d2h_bytes_per_step": evaluator.d2h_bytes()},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "frame_auc": res["AUC"], "frame_ap": res["AP"],
+        "forward_tflops_algorithmic": round(rows_local * world * FLOPS_PER_FRAME_T256 / (ms_dev * 1e-3) / 1e12, 2),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

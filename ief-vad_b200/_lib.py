@@ -40,10 +40,14 @@ _SIGS = {
     "iefvad_linear": (_i, [_vp] * 4 + [_f, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
     "iefvad_mha": (_i, [_vp] * 5 + [_i64, _i64, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "iefvad_classifier": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
-    "iefvad_mil_topk_mean": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp]),
-    "iefvad_clas2": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
-    "iefvad_auc_ap": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
-    "iefvad_sort_scores": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "iefvad_mil_topk_mean": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _vp]),
+    "iefvad_clas2": (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "iefvad_sort_scores": (_i, [_vp, _i64, _vp, _vp]),
+    "iefvad_auc_ap": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "iefvad_segment_copy": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "iefvad_launch_count": (C.c_uint64, []),
+    "iefvad_profile_enable": (_i, [_i]),
+    "iefvad_profile_read": (_i, [_vp, _vp, _vp]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -310,6 +310,7 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
   dim3 grid((a.T + QB - 1) / QB, a.H, a.B);
   attn_tc_kernel<DH, DHP><<<grid, 192, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, a.attn_mask,
                                                                   a.key_pad);
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }
@@ -420,6 +421,7 @@ int attn_simt(const float* qkv, float* out, int B, int T, int H, int dh, const f
     case 128: attn_simt_kernel<128><<<grid, 128, 0, stream>>>(qkv, out, T, H, D, qscale, attn_mask, key_pad); break;
     default: set_error("attn_simt: unsupported head dim %d", dh); return IEFVAD_ERR_INVALID;
   }
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }

@@ -8,6 +8,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "model.cuh"
+#include "rank.cuh"
 
 namespace iefvad {
 const char* last_error();
@@ -255,6 +256,49 @@ int iefvad_classifier(const float* x, int64_t rows, int dim, const float* w, con
   int sms = 0;
   IEF_TRY(current_sms(&sms));
   return classifier(x, rows, dim, w, bias, logits, scores, sms, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_mil_topk_mean(const float* x, const int64_t* lengths, int64_t B, int64_t T, int apply_sigmoid, float* mean,
+                         int32_t* idx, int kmax, void* stream) {
+  return mil_topk_mean(x, reinterpret_cast<const long long*>(lengths), B, T, apply_sigmoid, mean, idx, kmax,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_clas2(const float* logits, const float* labels, int64_t label_stride, const int64_t* lengths, int64_t B,
+                 int64_t T, float* means, float* loss, void* stream) {
+  return clas2(logits, labels, label_stride, reinterpret_cast<const long long*>(lengths), B, T, means, loss,
+               static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_sort_scores(const float* scores, int64_t n, int32_t* order, void* stream) {
+  return sort_scores(scores, n, order, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_auc_ap(const float* scores, const int32_t* pos, int64_t n, int repeat, double* out, int32_t* order,
+                  void* stream) {
+  return auc_ap(scores, pos, n, repeat, out, order, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, const int64_t* dst_off,
+                        const int64_t* len, int64_t nseg, void* stream) {
+  return segment_copy(src, reinterpret_cast<const long long*>(src_off), dst,
+                      reinterpret_cast<const long long*>(dst_off), reinterpret_cast<const long long*>(len), nseg,
+                      static_cast<cudaStream_t>(stream));
+}
+
+uint64_t iefvad_launch_count(void) { return launch_count(); }
+
+int iefvad_profile_enable(int on) {
+  profiler().on = on != 0;
+  return IEFVAD_OK;
+}
+
+int iefvad_profile_read(double* ms, double* work, int64_t* launches) {
+  IEF_CHECK(ms && work && launches, "iefvad_profile_read: null argument");
+  long long l[KC_COUNT];
+  IEF_TRY(profiler().read(ms, work, l));
+  for (int i = 0; i < KC_COUNT; ++i) launches[i] = l[i];
+  return IEFVAD_OK;
 }
 
 }  // extern "C"

@@ -212,6 +212,7 @@ int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi,
       set_error("ingest: unsupported dtype code %d (0 = f32, 1 = f16, 2 = bf16)", dtype);
       return IEFVAD_ERR_INVALID;
   }
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }
@@ -230,6 +231,7 @@ int layernorm(const float* x, long long M, int D, const float* w1, const float* 
     IEF_LN(1) IEF_LN(2) IEF_LN(3) IEF_LN(4) IEF_LN(5) IEF_LN(6) IEF_LN(7) IEF_LN(8)
   }
 #undef IEF_LN
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }
@@ -245,6 +247,7 @@ int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* l
       reinterpret_cast<const float4*>(lv_i), reinterpret_cast<const float4*>(lv_e), n4, factor, eps,
       reinterpret_cast<float4*>(w_i), reinterpret_cast<float4*>(w_e), reinterpret_cast<float4*>(fused), fused_hi,
       fused_lo);
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }
@@ -254,6 +257,7 @@ int classifier(const float* x, long long M, int D, const float* w, const float* 
   IEF_CHECK(D % 4 == 0, "classifier: D=%d must be a multiple of 4", D);
   if (M == 0) return IEFVAD_OK;
   classifier_kernel<<<grid_for(M * 32, num_sms), kThreads, 0, stream>>>(x, M, D, w, bias, logits, scores);
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }

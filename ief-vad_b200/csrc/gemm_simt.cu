@@ -72,6 +72,7 @@ int gemm_simt(const float* A, int lda, const float* W, int ldw, int M, int N, in
             "gemm_simt: need K %% 16 == 0, N %% 8 == 0, lda/ldw %% 4 == 0 (K=%d N=%d)", K, N);
   dim3 grid((M + SBM - 1) / SBM, (N + SBN - 1) / SBN);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(A, lda, W, ldw, M, N, K, ep);
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }

@@ -192,6 +192,7 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, g.M, g.N, g.K, g.nsplit, ep);
+  count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }

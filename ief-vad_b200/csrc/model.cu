@@ -29,6 +29,52 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
+Profiler& profiler() {
+  static Profiler p;
+  return p;
+}
+
+void Profiler::begin(int cls, double work, cudaStream_t st) {
+  if (!on) return;
+  Rec r;
+  r.cls = cls;
+  r.work = work;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  recs.push_back(r);
+}
+
+void Profiler::end(cudaStream_t st) {
+  if (!on || recs.empty()) return;
+  cudaEventRecord(recs.back().b, st);
+}
+
+int Profiler::read(double* ms, double* work, long long* launches) {
+  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0.0; work[i] = 0.0; launches[i] = 0; }
+  for (auto& r : recs) {
+    IEF_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    IEF_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t;
+    work[r.cls] += r.work;
+    launches[r.cls] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  recs.clear();
+  return IEFVAD_OK;
+}
+
+// time one launch when profiling is on (no-op otherwise)
+#define IEF_PROF(cls, work, call)          \
+  do {                                     \
+    profiler().begin(cls, work, stream);   \
+    int _prc = (call);                     \
+    profiler().end(stream);                \
+    if (_prc != 0) return _prc;            \
+  } while (0)
+
 int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, float lambda, int noise_model, float nu,
                 float epsilon) {
   IEF_CHECK(embed_dim >= 128 && embed_dim % 128 == 0 && embed_dim <= 1024,
@@ -194,9 +240,9 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
                    float* scores, cudaStream_t stream) {
   IEF_TRY(check_loaded());
   IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
+  if (B == 0 || T == 0) return IEFVAD_OK;
   IEF_CHECK(img && ev && fused && logits && image_mu && event_mu && image_logvar && event_logvar && w_i && w_e,
             "forward: null tensor pointer");
-  if (B == 0 || T == 0) return IEFVAD_OK;
   IEF_CHECK(T <= (1 << 24), "T=%lld too long", T);
   const bool fp32_plan = plan < 0;
   const size_t in_esize = (in_dtype == IEFVAD_DT_F32) ? 4 : 2;
@@ -218,7 +264,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     const long long row0 = b0 * T;
     for (int m = 0; m < 2; ++m) {
       const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + size_t(row0) * D * in_esize;
-      IEF_TRY(ingest(in, in_dtype, M * D, x32.as<float>(), fp32_plan ? nullptr : a_hi.as<bf16>(),
+      IEF_PROF(KC_INGEST, double(M) * D * (in_esize + 4 + 2), ingest(in, in_dtype, M * D, x32.as<float>(), fp32_plan ? nullptr : a_hi.as<bf16>(),
                      (!fp32_plan && (plan & PLAN_SPLIT_ENCODER)) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
       for (int i = 0; i < L; ++i) {                                   // model/imf_vad.py:114-116 / :120-122
         const Linear& ip = in_proj[m][i];
@@ -227,12 +273,12 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
         if (fp32_plan) {
           EpiParams e1;
           e1.bias = ip.b; e1.out_f32 = qkv32.as<float>(); e1.ld_f32 = 3 * D;
-          IEF_TRY(gemm_simt(x32.as<float>(), D, ip.w, D, int(M), 3 * D, D, e1, stream));
-          IEF_TRY(attn_simt(qkv32.as<float>(), attn32.as<float>(), Bs, int(T), H, dh, nullptr, nullptr, stream));
+          IEF_PROF(KC_GEMM_SIMT, 6.0 * M * D * D, gemm_simt(x32.as<float>(), D, ip.w, D, int(M), 3 * D, D, e1, stream));
+          IEF_PROF(KC_ATTN_SIMT, 4.0 * M * T * D, attn_simt(qkv32.as<float>(), attn32.as<float>(), Bs, int(T), H, dh, nullptr, nullptr, stream));
           EpiParams e2;
           e2.bias = op.b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.out_f32 = y32.as<float>(); e2.ld_f32 = D;
-          IEF_TRY(gemm_simt(attn32.as<float>(), D, op.w, D, int(M), D, D, e2, stream));
-          IEF_TRY(layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
+          IEF_PROF(KC_GEMM_SIMT, 2.0 * M * D * D, gemm_simt(attn32.as<float>(), D, op.w, D, int(M), D, D, e2, stream));
+          IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
                             last ? whiten_b[m] : nullptr, 1e-5f, x32.as<float>(), nullptr, nullptr, num_sms, stream));
         } else {
           const bool sp = (plan & PLAN_SPLIT_ENCODER) != 0;
@@ -242,26 +288,26 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           GemmTcArgs g1;
           g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = ip.w_hi; g1.W_lo = ip.w_lo;
           g1.M = int(M); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1;
-          IEF_TRY(gemm_tc(g1, e1, num_sms, stream));
+          IEF_PROF(KC_GEMM_TC, 6.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
           AttnTcArgs at;
           at.q = qb.as<bf16>(); at.k = kb.as<bf16>(); at.vt = vtb.as<bf16>(); at.out = h_hi.as<bf16>(); at.ldo = D;
           at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
-          IEF_TRY(attn_tc(at, stream));
+          IEF_PROF(KC_ATTN_TC, 4.0 * M * T * D, attn_tc(at, stream));
           EpiParams e2;
           e2.bias = op.b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.out_f32 = y32.as<float>(); e2.ld_f32 = D;
           GemmTcArgs g2;
           g2.A_hi = h_hi.as<bf16>(); g2.W_hi = op.w_hi; g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
-          IEF_TRY(gemm_tc(g2, e2, num_sms, stream));
+          IEF_PROF(KC_GEMM_TC, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
           // LN_i (+ whitening LN after the last layer, :117/:123); bf16 hi(/lo) feed the next GEMM
           const bool need_lo = last ? (plan & PLAN_SPLIT_HEADS) != 0 : sp;
-          IEF_TRY(layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
+          IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
                             last ? whiten_b[m] : nullptr, 1e-5f, last ? nullptr : x32.as<float>(), a_hi.as<bf16>(),
                             need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream));
         }
       }
       if (L == 0) {
         // no attention layers: only the whitening LN (model/imf_vad.py:117)
-        IEF_TRY(layernorm(x32.as<float>(), M, D, whiten_w[m], whiten_b[m], nullptr, nullptr, 1e-5f,
+        IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(x32.as<float>(), M, D, whiten_w[m], whiten_b[m], nullptr, nullptr, 1e-5f,
                           fp32_plan ? y32.as<float>() : nullptr, fp32_plan ? nullptr : a_hi.as<bf16>(),
                           (!fp32_plan && (plan & PLAN_SPLIT_HEADS)) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
         if (fp32_plan) IEF_CUDA(cudaMemcpyAsync(x32.p, y32.p, size_t(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
@@ -271,20 +317,20 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       eh.bias = heads[m].b; eh.out_f32 = mu_out[m] + row0 * D; eh.out_f32_b = lv_out[m] + row0 * D; eh.ld_f32 = D;
       eh.split_col = D;
       if (fp32_plan) {
-        IEF_TRY(gemm_simt(x32.as<float>(), D, heads[m].w, D, int(M), 2 * D, D, eh, stream));
+        IEF_PROF(KC_GEMM_SIMT, 4.0 * M * D * D, gemm_simt(x32.as<float>(), D, heads[m].w, D, int(M), 2 * D, D, eh, stream));
       } else {
         GemmTcArgs gh;
         gh.A_hi = a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>(); gh.W_hi = heads[m].w_hi; gh.W_lo = heads[m].w_lo;
         gh.M = int(M); gh.N = 2 * D; gh.K = D; gh.lda = D; gh.ldw = D;
         gh.nsplit = (plan & PLAN_SPLIT_HEADS) ? 3 : 1;
-        IEF_TRY(gemm_tc(gh, eh, num_sms, stream));
+        IEF_PROF(KC_GEMM_TC, 4.0 * M * D * D, gemm_tc(gh, eh, num_sms, stream));
       }
     }
     // uncertainty-weighted fusion (:130-144)
     const bool rsp = !fp32_plan && (plan & PLAN_SPLIT_REFINE);
     float* fused_out = fused + row0 * D;
     float* xcur = (R == 0) ? fused_out : x32.as<float>();
-    IEF_TRY(fuse(image_mu + row0 * D, event_mu + row0 * D, image_logvar + row0 * D, event_logvar + row0 * D, M * D,
+    IEF_PROF(KC_FUSE, double(M) * D * 28, fuse(image_mu + row0 * D, event_mu + row0 * D, image_logvar + row0 * D, event_logvar + row0 * D, M * D,
                  factor, eps, w_i + row0 * D, w_e + row0 * D, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
                  (rsp && R > 0) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
     // iterative refinement (:146-149): x <- x - lambda * (W2 relu(W1 x + b1) + b2)
@@ -294,11 +340,11 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       if (fp32_plan) {
         EpiParams e1;
         e1.bias = ref1[i].b; e1.act = ACT_RELU; e1.out_f32 = h32.as<float>(); e1.ld_f32 = D;
-        IEF_TRY(gemm_simt(x32.as<float>(), D, ref1[i].w, D, int(M), D, D, e1, stream));
+        IEF_PROF(KC_GEMM_SIMT, 2.0 * M * D * D, gemm_simt(x32.as<float>(), D, ref1[i].w, D, int(M), D, D, e1, stream));
         EpiParams e2;
         e2.bias = ref2[i].b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.alpha = -lambda_ref;
         e2.out_f32 = xnext; e2.ld_f32 = D;
-        IEF_TRY(gemm_simt(h32.as<float>(), D, ref2[i].w, D, int(M), D, D, e2, stream));
+        IEF_PROF(KC_GEMM_SIMT, 2.0 * M * D * D, gemm_simt(h32.as<float>(), D, ref2[i].w, D, int(M), D, D, e2, stream));
       } else {
         EpiParams e1;
         e1.bias = ref1[i].b; e1.act = ACT_RELU; e1.out_hi = h_hi.as<bf16>(); e1.out_lo = rsp ? h_lo.as<bf16>() : nullptr;
@@ -306,7 +352,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
         GemmTcArgs g1;
         g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = ref1[i].w_hi; g1.W_lo = ref1[i].w_lo;
         g1.M = int(M); g1.N = D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = rsp ? 3 : 1;
-        IEF_TRY(gemm_tc(g1, e1, num_sms, stream));
+        IEF_PROF(KC_GEMM_TC, 2.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
         EpiParams e2;
         e2.bias = ref2[i].b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.alpha = -lambda_ref;
         e2.out_f32 = xnext; e2.ld_f32 = D;
@@ -314,11 +360,11 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
         GemmTcArgs g2;
         g2.A_hi = h_hi.as<bf16>(); g2.A_lo = h_lo.as<bf16>(); g2.W_hi = ref2[i].w_hi; g2.W_lo = ref2[i].w_lo;
         g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D; g2.nsplit = rsp ? 3 : 1;
-        IEF_TRY(gemm_tc(g2, e2, num_sms, stream));
+        IEF_PROF(KC_GEMM_TC, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
       }
     }
     // classifier (:150) stays fp32 in every plan
-    IEF_TRY(classifier(fused_out, M, D, cls_w, cls_b, logits + row0, scores ? scores + row0 : nullptr, num_sms, stream));
+    IEF_PROF(KC_CLASSIFIER, double(M) * D * 4, classifier(fused_out, M, D, cls_w, cls_b, logits + row0, scores ? scores + row0 : nullptr, num_sms, stream));
   }
   return IEFVAD_OK;
 }

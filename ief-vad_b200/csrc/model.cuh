@@ -76,12 +76,17 @@ struct Model {
   void destroy();
 };
 
-// Multi-head self-attention block on a slab, shared with the model/module.py Transformer (D4):
-//   plan >= 0: a_hi (+a_lo) -> QKV tcgen05 GEMM -> attn_tc -> ctx_hi [M, D] bf16
-//   plan <  0: x32 -> fp32 GEMM -> attn_simt -> ctx32 [M, D] fp32
-struct MhaScratch {
-  bf16 *q, *k, *vt;          // TC plan operand layouts
-  float *qkv32;              // fp32 plan
+// Per-kernel-class device timing (CUDA events on the launching stream) for bench.py's roofline block.
+enum : int { KC_GEMM_TC = 0, KC_ATTN_TC, KC_LAYERNORM, KC_FUSE, KC_CLASSIFIER, KC_INGEST, KC_GEMM_SIMT, KC_ATTN_SIMT,
+             KC_COUNT };
+struct Profiler {
+  bool on = false;
+  struct Rec { int cls; double work; cudaEvent_t a, b; };   // work = algorithmic flops (GEMM/attn) or bytes (others)
+  std::vector<Rec> recs;
+  void begin(int cls, double work, cudaStream_t st);
+  void end(cudaStream_t st);
+  int read(double* ms, double* work, long long* launches);     // synchronises, sums per class, clears
 };
+Profiler& profiler();
 
 }  // namespace iefvad

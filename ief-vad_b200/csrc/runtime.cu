@@ -1,4 +1,5 @@
 // Error plumbing + tensor-map encoding shared by all translation units of libiefvad.so.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -21,6 +22,10 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d in `%s`", static_cast<int>(e), cudaGetErrorString(e), file, line, what);

@@ -1,0 +1,203 @@
+"""Batched evaluation around the forward - what the reference's per-video Python loop does
+(train/ucf_test.py:70-178, 336-353; train/xd_test.py; test.py:76-174), restructured for one or many B200s:
+
+  * videos are chunked once with the reference's rule (data/tools.py:100-114: int(T/256)+1 zero-padded chunks of
+    256, an extra all-zero chunk when T % 256 == 0) and all chunks of all videos of a rank go through ONE forward
+    call `[sum S_v, 256, D]` (the library slabs it internally) instead of one launch sequence per video;
+  * the valid rows (`logits[:len_cur]`, :112-114) are compacted on the device, never concatenated on the host;
+  * multi-GPU: videos are independent, so ranks take disjoint video subsets (longest-processing-time greedy on the
+    chunk count) with no data-path collective; the only exchange is one `all_gather` of the padded per-rank score
+    vectors, after which every rank re-orders them into list order and computes AUC / AP, Ano-AUC and the class-wise
+    AUC / AP with the radix-sort + scan kernels (exact-integer tie handling, float64 final division).
+
+The class only orchestrates: chunking indices are built once on the host, every per-frame operation runs in
+libiefvad.so kernels."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+NORMAL_KEYS = ("Normal", "normal")
+
+
+def num_chunks(T: int, maxlen: int = 256) -> int:
+    """data/tools.py:100-114 + train/ucf_test.py:79-81."""
+    return 1 if T < maxlen else int(T / maxlen) + 1
+
+
+def partition_videos(lengths: Sequence[int], world: int, maxlen: int = 256) -> List[List[int]]:
+    """Deterministic LPT assignment of videos to ranks by chunk count (ties by index)."""
+    order = sorted(range(len(lengths)), key=lambda v: (-num_chunks(int(lengths[v]), maxlen), v))
+    load = [0] * world
+    parts: List[List[int]] = [[] for _ in range(world)]
+    for v in order:
+        r = min(range(world), key=lambda i: (load[i], i))
+        parts[r].append(v)
+        load[r] += num_chunks(int(lengths[v]), maxlen)
+    for p in parts:
+        p.sort()
+    return parts
+
+
+def gather_layout(lengths: Sequence[int], parts: List[List[int]]):
+    """Index arithmetic of the single collective.  Rank r packs the valid scores of its videos back to back into a
+    vector padded to max_count; after all_gather the concatenation [world * max_count] is re-ordered into list order
+    by segment copies (src offset in the gathered buffer, dst offset in list order, length) - one entry per video.
+    Pure host function (numpy), shared by the CUDA evaluator and the CPU/gloo test of the sharding logic."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    global_off = np.concatenate([[0], np.cumsum(lengths)])[:-1]
+    counts = [int(lengths[p].sum()) if len(p) else 0 for p in parts]
+    max_count = max(counts) if counts else 0
+    src, dst, ln = [], [], []
+    for r, p in enumerate(parts):
+        off = 0
+        for v in p:
+            src.append(r * max(max_count, 1) + off)
+            dst.append(int(global_off[v]))
+            ln.append(int(lengths[v]))
+            off += int(lengths[v])
+    return (np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64), np.asarray(ln, dtype=np.int64),
+            counts, max_count)
+
+
+def _segment_copy(src, src_off, dst, dst_off, length):
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib.iefvad_segment_copy(src.data_ptr(), src_off.data_ptr(), dst.data_ptr(), dst_off.data_ptr(),
+                                                length.data_ptr(), src_off.numel(),
+                                                torch.cuda.current_stream(src.device).cuda_stream))
+
+
+class Evaluator:
+    """Frame-level evaluation of one video list on `world` GPUs (one process per GPU).
+
+    lengths[v] = embedding rows T_v, classes[v] = class key, gt = 0/1 per raw frame (16 per row) in list order."""
+
+    def __init__(self, model, lengths: Sequence[int], classes: Sequence[str], gt, *, maxlen: int = 256, repeat: int = 16,
+                 rank: int = 0, world: int = 1, device: Optional[torch.device] = None, process_group=None):
+        self.model = model
+        self.maxlen, self.repeat = maxlen, repeat
+        self.rank, self.world, self.group = rank, world, process_group
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lengths = np.asarray(lengths, dtype=np.int64)
+        self.classes = list(classes)
+        n = len(self.lengths)
+        assert len(self.classes) == n
+        self.total_rows = int(self.lengths.sum())
+        gt = np.asarray(gt)
+        if gt.size != repeat * self.total_rows:
+            raise ValueError(f"gt has {gt.size} frames, expected {repeat} x {self.total_rows}")
+        self.global_off = np.concatenate([[0], np.cumsum(self.lengths)])[:-1]
+        self.parts = partition_videos(self.lengths, world, maxlen)
+        self.mine = self.parts[rank]
+        g_src, g_dst, g_len, self.counts, self.max_count = gather_layout(self.lengths, self.parts)
+        dev = self.device
+        i64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int64), device=dev)  # noqa: E731
+        # local layout: chunk-row offset of each of my videos inside my [sum S, maxlen] score matrix
+        my_chunks = np.array([num_chunks(int(self.lengths[v]), maxlen) for v in self.mine], dtype=np.int64)
+        self.local_chunks = int(my_chunks.sum())
+        self.my_rows = int(self.lengths[self.mine].sum()) if len(self.mine) else 0
+        self.chunk_row0 = np.concatenate([[0], np.cumsum(my_chunks)])[:-1] * maxlen
+        self._src_off = i64(self.chunk_row0)
+        self._dst_off = i64(np.concatenate([[0], np.cumsum(self.lengths[self.mine])])[:-1] if len(self.mine) else [])
+        self._len = i64(self.lengths[self.mine] if len(self.mine) else [])
+        # gather layout: rank r's padded vector holds its videos back to back
+        self._g_src, self._g_dst, self._g_len = i64(g_src), i64(g_dst), i64(g_len)
+        # labels: positives per embedding row (gt is 16 raw frames per row, list/ucf_generate_gt.py:24)
+        self.pos = torch.as_tensor(gt.reshape(-1, repeat).sum(axis=1).astype(np.int32), device=dev)
+        # class-wise / Ano-AUC subsets (train/ucf_test.py:164-178, 336-353), as segment-copy index lists
+        self.subsets: Dict[str, tuple] = {}
+        keys = list(dict.fromkeys(self.classes))
+        groups = {k: [v for v in range(n) if self.classes[v] == k] for k in keys}
+        groups["__abnormal__"] = [v for v in range(n) if self.classes[v] not in NORMAL_KEYS]
+        for k, vids in groups.items():
+            if not vids:
+                continue
+            ln = self.lengths[vids]
+            dst = np.concatenate([[0], np.cumsum(ln)])[:-1]
+            pos_sub = torch.cat([self.pos[int(self.global_off[v]):int(self.global_off[v] + self.lengths[v])] for v in vids])
+            self.subsets[k] = (i64(self.global_off[vids]), i64(dst), i64(ln), int(ln.sum()), pos_sub.contiguous())
+        self._img = self._ev = None
+        self._pinned = None
+
+    # ------------------------------------------------------------------ feature staging
+    def chunk_features(self, feats: Sequence[torch.Tensor], dtype=torch.float16, pin: bool = False) -> torch.Tensor:
+        """Host: my videos' [T_v, D] features -> one zero-padded [sum S_v, maxlen, D] tensor (process_split rule)."""
+        D = feats[0].shape[1] if len(feats) else self.model.embed_dim
+        out = torch.zeros((self.local_chunks, self.maxlen, D), dtype=dtype, pin_memory=pin)
+        flat = out.view(-1, D)
+        for i, f in enumerate(feats):
+            r0 = int(self.chunk_row0[i])
+            flat[r0:r0 + f.shape[0]] = torch.nan_to_num(f, nan=0.0).to(dtype)     # train/ucf_test.py:83-88
+        return out
+
+    def set_device_features(self, img_chunks: torch.Tensor, ev_chunks: torch.Tensor) -> None:
+        self._img, self._ev = img_chunks.to(self.device), ev_chunks.to(self.device)
+
+    def set_host_features(self, img_chunks: torch.Tensor, ev_chunks: torch.Tensor) -> None:
+        """Pinned host staging for the end-to-end path (H2D inside every step)."""
+        self._pinned = (img_chunks if img_chunks.is_pinned() else img_chunks.pin_memory(),
+                        ev_chunks if ev_chunks.is_pinned() else ev_chunks.pin_memory())
+        self._img = torch.empty(self._pinned[0].shape, dtype=self._pinned[0].dtype, device=self.device)
+        self._ev = torch.empty_like(self._img)
+
+    # ------------------------------------------------------------------ one evaluation pass
+    def local_scores(self) -> torch.Tensor:
+        """Forward over all my chunks -> compacted sigmoid scores of my valid rows (device, fp32)."""
+        packed = torch.empty(max(self.max_count, 1), dtype=torch.float32, device=self.device)
+        if self.local_chunks:
+            out = self.model.temporal(self._img, self._ev, with_scores=True)
+            _segment_copy(out["scores"], self._src_off, packed, self._dst_off, self._len)
+        return packed
+
+    def gather(self, packed: torch.Tensor) -> torch.Tensor:
+        """The single collective: all ranks' padded score vectors -> list-order score vector on every rank."""
+        if self.world > 1:
+            import torch.distributed as dist
+            allv = torch.empty(self.world * max(self.max_count, 1), dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(allv, packed, group=self.group)
+        else:
+            allv = packed
+        scores = torch.empty(self.total_rows, dtype=torch.float32, device=self.device)
+        if self.total_rows:
+            _segment_copy(allv, self._g_src, scores, self._g_dst, self._g_len)
+        return scores
+
+    def metrics(self, scores: torch.Tensor) -> Dict[str, object]:
+        """AUC / AP overall, Ano-AUC and class-wise AUC / AP; one device->host read at the end."""
+        outs = [ops.auc_ap(scores, self.pos, self.repeat)]
+        names = ["__all__"]
+        for k, (src, dst, ln, total, pos_sub) in self.subsets.items():
+            sub = torch.empty(total, dtype=torch.float32, device=self.device)
+            _segment_copy(scores, src, sub, dst, ln)
+            outs.append(ops.auc_ap(sub, pos_sub, self.repeat))
+            names.append(k)
+        table = torch.stack(outs).cpu().numpy()
+        res: Dict[str, object] = {"AUC": float(table[0, 0]), "AP": float(table[0, 1]), "ano_AUC": float("nan"),
+                                  "classwise": {}}
+        for name, row in zip(names[1:], table[1:]):
+            if name == "__abnormal__":
+                res["ano_AUC"] = float(row[0])          # NaN when only one label value is present (:347-350)
+            elif row[2] > 0:                            # classes without positives are skipped (:167-168)
+                res["classwise"][name] = (float(row[0]), float(row[1]))
+        return res
+
+    def step(self, host_inputs: bool = False, with_metrics: bool = True) -> Dict[str, object]:
+        if host_inputs:
+            self._img.copy_(self._pinned[0], non_blocking=True)
+            self._ev.copy_(self._pinned[1], non_blocking=True)
+        scores = self.gather(self.local_scores())
+        res = self.metrics(scores) if with_metrics else {}
+        res["scores"] = scores
+        return res
+
+    # bytes moved by a host-input step (for bench.py's e2e block)
+    def h2d_bytes(self) -> int:
+        return 2 * self.local_chunks * self.maxlen * self.model.embed_dim * (self._pinned[0].element_size()
+                                                                             if self._pinned else 2)
+
+    def d2h_bytes(self) -> int:
+        return (1 + len(self.subsets)) * 4 * 8

@@ -98,3 +98,62 @@ def classifier(x, w, bias, with_scores: bool = False):
         _lib.check(_lib.lib.iefvad_classifier(x.data_ptr(), rows, D, w.data_ptr(), bias.data_ptr(), logits.data_ptr(),
                                               _lib.ptr(scores), _stream(x)))
     return (logits, scores) if with_scores else logits
+
+
+def mil_topk_mean(x, lengths=None, apply_sigmoid: bool = False, return_indices: bool = False):
+    """train/loss.py:24-27 per row: mean of the int(len/16 + 1) largest of x[row, :len].  x [B, T] (or [B, T, 1]);
+    lengths [B] integer tensor (device).  Optionally also the chosen positions [B, kmax] (-1 padded),
+    descending value, ties by ascending position."""
+    x = _f32c(x, "mil_topk_mean")
+    if x.dim() == 3 and x.shape[-1] == 1:
+        x = x[..., 0]
+    B, T = x.shape
+    x = x.contiguous()
+    if lengths is not None:
+        lengths = lengths.to(device=x.device, dtype=torch.int64).contiguous()
+    mean = torch.empty(B, dtype=torch.float32, device=x.device)
+    kmax = T // 16 + 1
+    idx = torch.empty((B, kmax), dtype=torch.int32, device=x.device) if return_indices else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_mil_topk_mean(x.data_ptr(), _lib.ptr(lengths), B, T, int(apply_sigmoid),
+                                                 mean.data_ptr(), _lib.ptr(idx), kmax, _stream(x)))
+    return (mean, idx) if return_indices else mean
+
+
+def clas2(logits, labels, lengths):
+    """train/loss.py:18-30 -> (loss scalar tensor, per-row means)."""
+    x = _f32c(logits, "clas2")
+    B, T = x.shape[0], x.shape[1]
+    x = x.reshape(B, T).contiguous()
+    labels = _f32c(labels.to(x.device), "clas2")
+    lengths = lengths.to(device=x.device, dtype=torch.int64).contiguous()
+    means = torch.empty(B, dtype=torch.float32, device=x.device)
+    loss = torch.empty((), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_clas2(x.data_ptr(), labels.data_ptr(), labels.stride(0), lengths.data_ptr(), B, T,
+                                         means.data_ptr(), loss.data_ptr(), _stream(x)))
+    return loss, means
+
+
+def sort_scores(scores) -> torch.Tensor:
+    """Stable descending argsort (int32) == np.argsort(-scores, kind='stable')."""
+    s = _f32c(scores, "sort_scores").reshape(-1)
+    order = torch.empty(s.numel(), dtype=torch.int32, device=s.device)
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib.iefvad_sort_scores(s.data_ptr(), s.numel(), order.data_ptr(), _stream(s)))
+    return order
+
+
+def auc_ap(scores, pos, repeat: int = 16, return_order: bool = False):
+    """-> float64 tensor [4] on the device: AUC, AP, #positive frames, #negative frames (train/ucf_test.py:151-152
+    on np.repeat(scores, repeat)); pos[j] = positives among segment j's `repeat` frames."""
+    s = _f32c(scores, "auc_ap").reshape(-1)
+    p = pos.to(device=s.device, dtype=torch.int32).contiguous().reshape(-1)
+    if p.numel() != s.numel():
+        raise RuntimeError(f"auc_ap: {s.numel()} scores but {p.numel()} label counts")
+    out = torch.empty(4, dtype=torch.float64, device=s.device)
+    order = torch.empty(s.numel(), dtype=torch.int32, device=s.device) if return_order else None
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib.iefvad_auc_ap(s.data_ptr(), p.data_ptr(), s.numel(), repeat, out.data_ptr(),
+                                          _lib.ptr(order), _stream(s)))
+    return (out, order) if return_order else out

@@ -77,9 +77,9 @@ int iefvad_model_forward(iefvad_model* m, const void* img, const void* ev, int i
                          float* event_logvar, float* w_i, float* w_e, float* scores, void* stream);
 
 /* Same path with HOST buffers: copies img / ev host->device, runs the forward, copies logits (and, when
- * non-NULL, scores) device->host and synchronises the stream.  The seven wide outputs stay on the device in
- * caller-provided DEVICE buffers (pass NULL to let the library keep them in scratch).  Host pointers should be
- * pinned for full copy bandwidth.  This is the call `bench.py` times for `e2e`. */
+ * non-NULL, scores) device->host and synchronises the stream.  The seven wide outputs stay in library-owned device
+ * scratch (the evaluation loop only consumes the scores).  Host pointers should be pinned for full copy bandwidth;
+ * batches larger than the slab size are streamed slab by slab. */
 int iefvad_model_forward_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
                               int64_t T, float* logits_host, float* scores_host, void* stream);
 
@@ -112,6 +112,53 @@ int iefvad_mha(const float* x, const float* in_w, const float* in_b, const float
 /* Linear(embed_dim -> 1), model/imf_vad.py:150 (+ optional sigmoid). */
 int iefvad_classifier(const float* x, int64_t rows, int dim, const float* w, const float* bias, float* logits,
                       float* scores, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MIL top-k pooling and frame-level AUC / AP
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per-row top-k mean of train/loss.py:24-27: k = int(len/16 + 1) largest of x[row, :len] (after sigmoid when
+ * apply_sigmoid != 0), averaged.  x [B, T] fp32 (T <= 16384); lengths [B] int64 (device; NULL = every row full).
+ * mean [B] fp32.  idx (optional) [B, kmax] int32: the selected positions in descending-value order, ties by
+ * ascending position, padded with -1. */
+int iefvad_mil_topk_mean(const float* x, const int64_t* lengths, int64_t B, int64_t T, int apply_sigmoid, float* mean,
+                         int32_t* idx, int kmax, void* stream);
+
+/* CLAS2 of train/loss.py:18-30: logits [B, T] (the [B, T, 1] logits tensor), labels [B, *] fp32 with row stride
+ * `label_stride` elements (column 0 = normal), lengths [B] int64.  means [B] and the scalar loss are written. */
+int iefvad_clas2(const float* logits, const float* labels, int64_t label_stride, const int64_t* lengths, int64_t B,
+                 int64_t T, float* means, float* loss, void* stream);
+
+/* Stable descending argsort of fp32 scores: order[i] = index of the i-th largest score, ties by ascending index
+ * (== numpy.argsort(-scores, kind="stable"), the ranking sklearn/metrics/_ranking.py builds). */
+int iefvad_sort_scores(const float* scores, int64_t n, int32_t* order, void* stream);
+
+/* roc_auc_score / average_precision_score (train/ucf_test.py:151-152) of np.repeat(scores, repeat) against labels
+ * in which segment j has pos[j] positive frames out of `repeat`.  scores [n] fp32, pos [n] int32,
+ * out: DEVICE double[4] = {AUC (NaN if one class only), AP, #positive frames, #negative frames};
+ * order (optional) [n] int32 receives the rank permutation. */
+int iefvad_auc_ap(const float* scores, const int32_t* pos, int64_t n, int repeat, double* out, int32_t* order,
+                  void* stream);
+
+/* Segmented copy: dst[dst_off[s] + i] = src[src_off[s] + i] for i < len[s] (all arrays on the device, int64).
+ * Drops the zero-pad rows of chunked videos (train/ucf_test.py:113 `logits1[0:len_cur]`), and re-orders the
+ * per-rank score vectors into list order after the multi-GPU gather. */
+int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, const int64_t* dst_off,
+                        const int64_t* len, int64_t nseg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Instrumentation used by bench.py
+ * ---------------------------------------------------------------------------------------------- */
+
+/* number of CUDA kernels this library has launched since load (process-wide) */
+uint64_t iefvad_launch_count(void);
+
+/* Per-kernel-class device timing of the model forward with CUDA events on the launching stream.
+ * classes: 0 gemm_tc, 1 attn_tc, 2 layernorm, 3 fuse, 4 classifier, 5 ingest, 6 gemm_simt, 7 attn_simt.
+ * iefvad_profile_read synchronises, fills ms / work (algorithmic FLOPs for classes 0, 1, 6, 7; algorithmic bytes
+ * otherwise) / launches (arrays of 8) for everything recorded since the last read, and clears the record. */
+int iefvad_profile_enable(int on);
+int iefvad_profile_read(double* ms, double* work, int64_t* launches);
 
 #ifdef __cplusplus
 }

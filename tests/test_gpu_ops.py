@@ -36,7 +36,8 @@ def test_fuse_matches_oracle(ops, noise, nu):
         got = got.cpu().numpy()
         finite = np.isfinite(ref)
         assert np.array_equal(np.isfinite(got), finite)
-        np.testing.assert_allclose(got[finite], ref[finite], rtol=1e-5, atol=1e-7)
+        # fused = w_i*mu_i + w_e*mu_e cancels, so its error is absolute (a few ulp of the O(1) products)
+        np.testing.assert_allclose(got[finite], ref[finite], rtol=1e-5, atol=1e-6)
 
 
 def test_fuse_rejects_unknown_noise_model_and_cpu_tensors(ops):
