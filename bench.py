@@ -53,8 +53,38 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml = None
+        self.samples = []
+        self._stop = threading.Event()
+
+    def _nvml_loop(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.index)
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self._stop.wait(0.05)
 
     def start(self):
+        # NVML in-process (cheap) - spawning nvidia-smi in a loop perturbs short timed regions
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -68,6 +98,14 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = [s[0] for s in self.samples]
+            mx = [s[1] for s in self.samples]
+            reasons = sorted({r for s in self.samples for r in s[2]})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, 50 ms period during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()

@@ -286,6 +286,67 @@ int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, co
                       static_cast<cudaStream_t>(stream));
 }
 
+int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int epi_kind, int iters, float* ms_per_iter) {
+  IEF_CHECK(M > 0 && M < (1LL << 31) && N > 0 && K > 0 && iters > 0 && ms_per_iter, "iefvad_bench_gemm: bad argument");
+  IEF_CHECK(epi_kind >= 0 && epi_kind <= 4, "iefvad_bench_gemm: epi_kind in [0, 4]");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  cudaStream_t st = nullptr;
+  Scratch sc(st);
+  void *ah, *al, *wh, *wl, *bias, *resid, *of, *oh, *ol, *q, *k, *vt;
+  const int H = 8, dh = N / 3 / H > 0 ? N / 3 / H : 1, dhp = (dh + 63) / 64 * 64;
+  const int T = 256, Tpad = 256;
+  IEF_TRY(sc.get(&ah, size_t(M) * K * 2));
+  IEF_TRY(sc.get(&al, size_t(M) * K * 2));
+  IEF_TRY(sc.get(&wh, size_t(N) * K * 2));
+  IEF_TRY(sc.get(&wl, size_t(N) * K * 2));
+  IEF_TRY(sc.get(&bias, size_t(N) * 4));
+  IEF_TRY(sc.get(&resid, size_t(M) * N * 4));
+  IEF_TRY(sc.get(&of, size_t(M) * N * 4));
+  IEF_TRY(sc.get(&oh, size_t(M) * N * 2));
+  IEF_TRY(sc.get(&ol, size_t(M) * N * 2));
+  IEF_CUDA(cudaMemsetAsync(ah, 0x3c, size_t(M) * K * 2, st));     // bf16 0x3c3c ~ 0.0115: finite, non-zero operands
+  IEF_CUDA(cudaMemsetAsync(al, 0x3a, size_t(M) * K * 2, st));
+  IEF_CUDA(cudaMemsetAsync(wh, 0x3c, size_t(N) * K * 2, st));
+  IEF_CUDA(cudaMemsetAsync(wl, 0x3a, size_t(N) * K * 2, st));
+  IEF_CUDA(cudaMemsetAsync(bias, 0, size_t(N) * 4, st));
+  IEF_CUDA(cudaMemsetAsync(resid, 0, size_t(M) * N * 4, st));
+  EpiParams ep;
+  ep.bias = static_cast<float*>(bias);
+  if (epi_kind == 0) ep.mode = EPI_DISCARD;
+  if (epi_kind == 1) { ep.out_f32 = (float*)of; ep.ld_f32 = N; }
+  if (epi_kind == 2) {
+    ep.resid = (float*)resid; ep.ld_resid = N; ep.alpha = -0.5f; ep.out_f32 = (float*)of; ep.ld_f32 = N;
+    ep.out_hi = (bf16*)oh; ep.out_lo = (bf16*)ol; ep.ld_bf = N;
+  }
+  if (epi_kind == 3) { ep.act = ACT_RELU; ep.out_hi = (bf16*)oh; ep.out_lo = (bf16*)ol; ep.ld_bf = N; }
+  if (epi_kind == 4) {
+    IEF_CHECK(N % (3 * H * 32) == 0 && M % T == 0, "iefvad_bench_gemm: qkv epilogue needs N = 3*8*dh, M %% 256 == 0");
+    IEF_TRY(sc.get(&q, size_t(M) * H * dhp * 2));
+    IEF_TRY(sc.get(&k, size_t(M) * H * dhp * 2));
+    IEF_TRY(sc.get(&vt, size_t(M) * H * dh * 2));
+    ep.mode = EPI_QKV; ep.q = (bf16*)q; ep.k = (bf16*)k; ep.vt = (bf16*)vt; ep.T = T; ep.H = H; ep.dh = dh; ep.dhp = dhp;
+    ep.Tpad = Tpad; ep.D = N / 3; ep.qscale = 0.1f;
+  }
+  GemmTcArgs g;
+  g.A_hi = (bf16*)ah; g.A_lo = (bf16*)al; g.W_hi = (bf16*)wh; g.W_lo = (bf16*)wl;
+  g.M = int(M); g.N = N; g.K = K; g.lda = K; g.ldw = K; g.nsplit = nsplit; g.force_bn = tile_n;
+  for (int i = 0; i < 3; ++i) IEF_TRY(gemm_tc(g, ep, sms, st));
+  cudaEvent_t e0, e1;
+  IEF_CUDA(cudaEventCreate(&e0));
+  IEF_CUDA(cudaEventCreate(&e1));
+  IEF_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) IEF_TRY(gemm_tc(g, ep, sms, st));
+  IEF_CUDA(cudaEventRecord(e1, st));
+  IEF_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  IEF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_iter = ms / iters;
+  return IEFVAD_OK;
+}
+
 uint64_t iefvad_launch_count(void) { return launch_count(); }
 
 int iefvad_profile_enable(int on) {

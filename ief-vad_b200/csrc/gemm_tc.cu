@@ -36,7 +36,9 @@ struct TcCfg {
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/;
+  static constexpr size_t kStageOff = size_t(kStages) * kStageBytes;          // epilogue transpose tiles (4 warps)
+  static constexpr size_t kBarOff = kStageOff + 4 * EPI_STAGE_WORDS * sizeof(float);
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + kBarOff + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -48,7 +50,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * Cfg::kStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -146,15 +148,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const long long row = (long long)m_blk * BM + quarter * 32 + lane;
+      const long long row0 = (long long)m_blk * BM + quarter * 32;
       const uint32_t t0 = tmem_base + uint32_t(as * BN) + (uint32_t(quarter * 32) << 16);
+      float* stage = reinterpret_cast<float*>(smem + Cfg::kStageOff) + (warp - 2) * EPI_STAGE_WORDS;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         tmem_ld32(t0 + uint32_t(c * 32), v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row < M && col0 < N) epi_store_row<32>(ep, row, col0, v);
+        if (row0 < M && col0 < N) epi_chunk_warp(ep, row0, col0, v, stage, lane, M);
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);

@@ -46,31 +46,34 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, int dtype, int swizzle) {
   auto fn = get_encode();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
     return IEFVAD_ERR_CUDA;
   }
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = (dtype == TM_F32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = (swizzle == TM_SWIZZLE_NONE) ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : (swizzle == TM_SWIZZLE_64B) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(out, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %u dims {%llu,%llu,%llu} box {%u,%u,%u} base %p",
-              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
-              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0, base);
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %u dims {%llu,%llu,%llu} box {%u,%u,%u} base %p "
+              "stride0 %llu", static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0, base,
+              (unsigned long long)strides[0]);
     return IEFVAD_ERR_CUDA;
   }
   return IEFVAD_OK;
 }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                 uint32_t box_inner, uint32_t box_outer) {
+                 uint32_t box_inner, uint32_t box_outer, int dtype, int swizzle) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
-  return encode(out, base, 2, dims, strides, box);
+  return encode(out, base, 2, dims, strides, box, dtype, swizzle);
 }
 
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
@@ -78,7 +81,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, box2};
-  return encode(out, base, 3, dims, strides, box);
+  return encode(out, base, 3, dims, strides, box, TM_BF16, TM_SWIZZLE_128B);
 }
 
 }  // namespace iefvad
