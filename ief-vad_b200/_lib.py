@@ -45,7 +45,7 @@ _SIGS = {
     "iefvad_sort_scores": (_i, [_vp, _i64, _vp, _vp]),
     "iefvad_auc_ap": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "iefvad_segment_copy": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "iefvad_bench_gemm": (_i, [_i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "iefvad_bench_gemm": (_i, [_i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "iefvad_launch_count": (C.c_uint64, []),
     "iefvad_profile_enable": (_i, [_i]),
     "iefvad_profile_read": (_i, [_vp, _vp, _vp]),

@@ -286,7 +286,8 @@ int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, co
                       static_cast<cudaStream_t>(stream));
 }
 
-int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int epi_kind, int iters, float* ms_per_iter) {
+int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,
+                      float* ms_per_iter) {
   IEF_CHECK(M > 0 && M < (1LL << 31) && N > 0 && K > 0 && iters > 0 && ms_per_iter, "iefvad_bench_gemm: bad argument");
   IEF_CHECK(epi_kind >= 0 && epi_kind <= 4, "iefvad_bench_gemm: epi_kind in [0, 4]");
   int sms = 0;
@@ -330,7 +331,7 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int epi_k
   }
   GemmTcArgs g;
   g.A_hi = (bf16*)ah; g.A_lo = (bf16*)al; g.W_hi = (bf16*)wh; g.W_lo = (bf16*)wl;
-  g.M = int(M); g.N = N; g.K = K; g.lda = K; g.ldw = K; g.nsplit = nsplit; g.force_bn = tile_n;
+  g.M = int(M); g.N = N; g.K = K; g.lda = K; g.ldw = K; g.nsplit = nsplit; g.force_bn = tile_n; g.force_stages = stages;
   for (int i = 0; i < 3; ++i) IEF_TRY(gemm_tc(g, ep, sms, st));
   cudaEvent_t e0, e1;
   IEF_CUDA(cudaEventCreate(&e0));

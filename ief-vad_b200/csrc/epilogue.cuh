@@ -130,73 +130,4 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& p, long long row,
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Warp-level epilogue of the tcgen05 GEMM: one warp owns a 32-row x 32-column accumulator chunk, delivered by
-// tcgen05.ld as thread == row (v[j] = column col0 + j of row row0 + lane).  Storing that layout directly makes
-// every warp store touch 32 different 128-byte lines with 16 bytes each; instead the chunk is transposed through a
-// per-warp smem tile (row stride 36 words: 16-byte aligned float4 writes and conflict-free column reads) so that
-// lane == column and every global load / store of a row is one fully coalesced 128-byte (fp32) or 64-byte (bf16)
-// access.  The V part of the QKV scatter keeps thread == row because its destination is transposed ([.., d, t]).
-// ------------------------------------------------------------------------------------------------
-constexpr int EPI_STAGE_LD = 36;                       // words per staged row
-constexpr int EPI_STAGE_WORDS = 32 * EPI_STAGE_LD;     // per warp
-
-__device__ __forceinline__ void epi_chunk_warp(const EpiParams& p, long long row0, int col0, float* v, float* stage,
-                                               int lane, long long M) {
-  if (p.mode == EPI_DISCARD) return;
-  const int nrows = (M - row0 >= 32) ? 32 : int(M - row0);      // rows of this chunk that exist (>= 1 by construction)
-  if (p.mode == EPI_QKV && col0 >= 2 * p.D) {
-    if (lane < nrows) epi_store_row<32>(p, row0 + lane, col0, v);  // V^T: consecutive lanes = consecutive t
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 32; j += 4)
-    *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-  __syncwarp();
-  const int col = col0 + lane;
-  const float bias = p.bias ? __ldg(p.bias + col) : 0.f;
-  if (p.mode == EPI_QKV) {
-    const int which = col0 / p.D;
-    const int c = col0 - which * p.D;
-    const int h = c / p.dh;
-    const int d = c - h * p.dh + lane;
-    const float s = (which == 0) ? p.qscale : 1.f;
-    bf16* base = (which == 0) ? p.q : p.k;
-#pragma unroll 4
-    for (int r = 0; r < nrows; ++r) {
-      const long long row = row0 + r;
-      const long long b = row / p.T;
-      const int t = int(row - b * p.T);
-      const float x = (stage[r * EPI_STAGE_LD + lane] + bias) * s;
-      const float xn = __shfl_down_sync(0xffffffffu, x, 1);
-      if ((lane & 1) == 0)
-        *reinterpret_cast<uint32_t*>(base + ((b * p.H + h) * p.T + t) * (long long)p.dhp + d) = pack_bf16x2(x, xn);
-    }
-    __syncwarp();
-    return;
-  }
-  const bool second = col0 >= p.split_col;
-  float* of = p.out_f32 ? (second ? p.out_f32_b + (col - p.split_col) : p.out_f32 + col) : nullptr;
-#pragma unroll 4
-  for (int r = 0; r < nrows; ++r) {
-    const long long row = row0 + r;
-    float x = apply_act(stage[r * EPI_STAGE_LD + lane] + bias, p.act);
-    if (p.resid) x = fmaf(p.alpha, x, p.resid[row * p.ld_resid + col]);
-    else x *= p.alpha;
-    if (of) of[row * p.ld_f32] = x;
-    if (p.out_hi) {
-      const bf16 h = __float2bfloat16_rn(x);
-      const float hf = __bfloat162float(h);
-      const float hn = __shfl_down_sync(0xffffffffu, hf, 1);
-      if (p.out_lo) {
-        const float l = x - hf;
-        const float ln = __shfl_down_sync(0xffffffffu, l, 1);
-        if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(p.out_lo + row * p.ld_bf + col) = pack_bf16x2(l, ln);
-      }
-      if ((lane & 1) == 0) *reinterpret_cast<uint32_t*>(p.out_hi + row * p.ld_bf + col) = pack_bf16x2(hf, hn);
-    }
-  }
-  __syncwarp();
-}
-
 }  // namespace iefvad

@@ -6,16 +6,24 @@
 //
 // Structure (one CTA per SM, persistent over output tiles, 192 threads):
 //   warp 0     TMA producer   : cp.async.bulk.tensor 128x64 (A) and BNx64 (W) bf16 boxes, 128B swizzle,
-//                               into a STAGES-deep smem ring guarded by full/empty mbarriers
+//                               into a smem ring guarded by full/empty mbarriers
 //   warp 1     MMA issuer     : one thread issues 4 x tcgen05.mma (128 x BN x 16) per k-block into one of two
 //                               TMEM accumulator buffers; tcgen05.commit releases smem slots / publishes tiles
-//   warps 2-5  epilogue       : tcgen05.ld 32x32b.x32 (thread == output row), fused bias / activation /
-//                               residual / bf16 hi+lo split / QKV scatter (epilogue.cuh), direct global stores
-// The two TMEM buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+//   warps 2-5  epilogue       : each warp owns 32 accumulator rows (its TMEM lane quarter) and walks them in
+//                               32-column chunks: tcgen05.ld (thread == row) -> bias / activation / residual /
+//                               bf16 hi+lo split in registers -> swizzled per-warp smem boxes -> TMA bulk tensor
+//                               stores.  The fp32 residual arrives the same way (TMA loads into a per-warp ring,
+//                               prefetched several chunks - and across tile boundaries - ahead), so no epilogue
+//                               thread ever waits on a global load and every byte of epilogue traffic is issued as
+//                               full 32x32 boxes by the copy engine.  Rows past M are clipped by the tensor maps.
+// The two TMEM buffers let the epilogue of tile i overlap the MMAs of tile i+1.  The smem that is left after the
+// per-warp epilogue boxes decides the depth of the operand ring (3 stages beside a residual ring, 4 otherwise).
 //
 // "split-bf16" (nsplit == 3): A ~= A_hi + A_lo, W ~= W_hi + W_lo and the product is accumulated as
 // A_hi.W_hi + A_hi.W_lo + A_lo.W_hi in the same fp32 accumulator - implemented as a 3x longer K loop whose
 // k-blocks pick the (A, W) tensor-map pair, so the pipeline is unchanged.
+#include <cstring>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "gemm.cuh"
@@ -27,34 +35,70 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int CW = 32;                        // epilogue chunk width (columns)
+constexpr int kMaxStages = 8;
+constexpr int kMaxResidSlots = 4;
+constexpr uint32_t kF32Box = 32 * CW * 4;     // one 32-row x 32-col fp32 box (128-byte rows, SWIZZLE_128B)
+constexpr uint32_t kBfBox = 32 * CW * 2;      // the same box in bf16 (64-byte rows, SWIZZLE_64B)
+constexpr uint32_t kBarBytes = 512;
+constexpr uint32_t kSmemLimit = 232448;       // 227 KB opt-in maximum per CTA on sm_100
+
+// everything the device epilogue needs besides the tensor maps
+struct TcEpi {
+  int mode = EPI_ROWMAJOR;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  float alpha = 1.f;
+  int has_resid = 0, has_f32 = 0, has_hi = 0, has_lo = 0;
+  int split_col = 1 << 30;
+  int nr = 0;              // residual ring depth (per warp)
+  int nob = 1;             // output boxes per kind (1 = wait for the previous store before refilling, 2 = ping-pong)
+  uint32_t warp_bytes = 0; // per-warp epilogue smem
+  int stages = 4;
+  // EPI_QKV
+  bf16* q = nullptr;
+  bf16* k = nullptr;
+  bf16* vt = nullptr;
+  int T = 0, H = 0, dh = 0, dhp = 0, Tpad = 0, D = 0;
+  float qscale = 1.f;
+  int qk_tma = 0;          // q / k leave through 4-D TMA stores (T % 32 == 0), else per-thread 16-byte stores
+};
+
+struct TcMaps {
+  CUtensorMap a0, a1, b0, b1;   // operands (hi / lo)
+  CUtensorMap r;                // fp32 residual [M, N]
+  CUtensorMap o0, o1;           // fp32 outputs (columns below / from split_col)
+  CUtensorMap h, l;             // bf16 hi / lo outputs; in EPI_QKV: q / k as 4-D {d, t, head, batch}
+};
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
-  static constexpr size_t kStageOff = size_t(kStages) * kStageBytes;          // epilogue transpose tiles (4 warps)
-  static constexpr size_t kBarOff = kStageOff + 4 * EPI_STAGE_WORDS * sizeof(float);
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + kBarOff + 256 /*barriers*/;
 };
+
+// swizzled 16-byte slot of (row, 16-byte group g) inside a TMA box whose rows are 128 B (fp32) or 64 B (bf16)
+__device__ __forceinline__ uint32_t sw128(int row, int g) { return uint32_t(row) * 128u + (uint32_t(g ^ (row & 7)) << 4); }
+__device__ __forceinline__ uint32_t sw64(int row, int g) { return uint32_t(row) * 64u + (uint32_t(g ^ ((row >> 1) & 3)) << 4); }
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               int M, int N, int K, int nsplit, EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nsplit, const TcEpi ep) {
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  const int STAGES = ep.stages;
+  uint8_t* epi_base = smem + size_t(STAGES) * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + 4 * ep.warp_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull_all = tempty + 2;                                  // [4 warps][kMaxResidSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_all + 4 * kMaxResidSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -65,11 +109,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int total_kb = kb_per_seg * nsplit;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmB0);
+    tma_prefetch_desc(&tm.a0);
+    tma_prefetch_desc(&tm.b0);
     if (nsplit > 1) {
-      tma_prefetch_desc(&tmA1);
-      tma_prefetch_desc(&tmB1);
+      tma_prefetch_desc(&tm.a1);
+      tma_prefetch_desc(&tm.b1);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -77,8 +121,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 4);
     }
+    for (int s = 0; s < 4 * kMaxResidSlots; ++s) mbar_init(&rfull_all[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -99,8 +144,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         for (int kb = 0; kb < total_kb; ++kb) {
           const int seg = kb / kb_per_seg, kk = kb - seg * kb_per_seg;
-          const CUtensorMap* ma = (seg == 2) ? &tmA1 : &tmA0;   // hi.hi, hi.lo, lo.hi
-          const CUtensorMap* mb = (seg == 1) ? &tmB1 : &tmB0;
+          const CUtensorMap* ma = (seg == 2) ? &tm.a1 : &tm.a0;   // hi.hi, hi.lo, lo.hi
+          const CUtensorMap* mb = (seg == 1) ? &tm.b1 : &tm.b0;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + size_t(s) * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
@@ -141,27 +186,186 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;         // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    uint8_t* wb = epi_base + size_t(warp - 2) * ep.warp_bytes;
+    uint8_t* Rb = wb;                                              // [nr] fp32 residual boxes
+    uint8_t* Ob = Rb + size_t(ep.nr) * kF32Box;                    // [nob] fp32 output boxes
+    uint8_t* Hb = Ob + (ep.has_f32 ? size_t(ep.nob) * kF32Box : 0);  // [nob] bf16 hi (or q / k) boxes
+    uint8_t* Lb = Hb + (ep.has_hi ? size_t(ep.nob) * kBfBox : 0);    // [nob] bf16 lo boxes
+    uint64_t* rfull = rfull_all + (warp - 2) * kMaxResidSlots;
+    const bool discard = ep.mode == EPI_DISCARD;
+    const bool any_store = !discard && (ep.has_f32 || ep.has_hi);
+
+    // residual prefetch cursor (lane 0): walks the same (tile, chunk) sequence as the consumer, nr chunks ahead
+    int pf_tile = blockIdx.x, pf_c = 0;
+    uint32_t pf_n = 0;
+    auto chunks_of = [&](int tile) {
+      const int n_blk = tile % num_n;
+      const int w = N - n_blk * BN;
+      return (w < BN ? w : BN) / CW;
+    };
+    auto prefetch_resid = [&]() {
+      if (pf_tile >= num_tiles) return;
+      const int m_blk = pf_tile / num_n, n_blk = pf_tile % num_n;
+      const int slot = int(pf_n % uint32_t(ep.nr));
+      mbar_arrive_expect_tx(&rfull[slot], kF32Box);
+      tma_load_2d(&tm.r, &rfull[slot], Rb + size_t(slot) * kF32Box, n_blk * BN + pf_c * CW, m_blk * BM + quarter * 32);
+      ++pf_n;
+      if (++pf_c == chunks_of(pf_tile)) { pf_c = 0; pf_tile += gridDim.x; }
+    };
+    if (ep.has_resid && lane == 0) {
+      tma_prefetch_desc(&tm.r);
+      for (int i = 0; i < ep.nr; ++i) prefetch_resid();
+    }
+    uint32_t n_cons = 0;       // residual chunks consumed
+    uint32_t n_out = 0;        // output chunks produced
+
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      const int nchunks = chunks_of(tile);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const long long row0 = (long long)m_blk * BM + quarter * 32;
+      const int row0 = m_blk * BM + quarter * 32;     // first row of this warp; this thread owns row0 + lane
       const uint32_t t0 = tmem_base + uint32_t(as * BN) + (uint32_t(quarter * 32) << 16);
-      float* stage = reinterpret_cast<float*>(smem + Cfg::kStageOff) + (warp - 2) * EPI_STAGE_WORDS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < nchunks; ++c) {
         float v[32];
-        tmem_ld32(t0 + uint32_t(c * 32), v);
+        tmem_ld32(t0 + uint32_t(c * CW), v);
         tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row0 < M && col0 < N) epi_chunk_warp(ep, row0, col0, v, stage, lane, M);
+        if (c == nchunks - 1) {           // accumulator fully in registers: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+        if (discard) continue;
+        const int col0 = n_blk * BN + c * CW;
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+        }
+
+        if (ep.mode == EPI_QKV) {
+          const int which = col0 / ep.D;                 // 0 = q, 1 = k, 2 = v (a chunk never straddles: D % 32 == 0)
+          const int cc = col0 - which * ep.D;
+          const int h = cc / ep.dh;                      // dh % 32 == 0 -> a chunk stays inside one head
+          const int d0 = cc - h * ep.dh;
+          const long long row = (long long)row0 + lane;
+          const long long b = row / ep.T;
+          const int t = int(row - b * ep.T);
+          if (which == 2) {
+            // V^T [B, H, dh, Tpad]: consecutive lanes = consecutive t, so each of the 32 stores is one 64-byte run
+            if (row < M) {
+              bf16* dst = ep.vt + ((b * ep.H + h) * ep.dh + d0) * (long long)ep.Tpad + t;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[(long long)j * ep.Tpad] = __float2bfloat16_rn(v[j]);
+            }
+            continue;
+          }
+          const float s = (which == 0) ? ep.qscale : 1.f;
+          uint4 u[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            u[g].x = pack_bf16x2(v[g * 8 + 0] * s, v[g * 8 + 1] * s);
+            u[g].y = pack_bf16x2(v[g * 8 + 2] * s, v[g * 8 + 3] * s);
+            u[g].z = pack_bf16x2(v[g * 8 + 4] * s, v[g * 8 + 5] * s);
+            u[g].w = pack_bf16x2(v[g * 8 + 6] * s, v[g * 8 + 7] * s);
+          }
+          if (!ep.qk_tma) {
+            if (row < M) {
+              bf16* dst = (which == 0 ? ep.q : ep.k) + ((b * ep.H + h) * ep.T + t) * (long long)ep.dhp + d0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + g * 8) = u[g];
+            }
+            continue;
+          }
+          const int ob = (ep.nob == 2) ? int(n_out & 1) : 0;
+          if (lane == 0) { if (ep.nob == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+          __syncwarp();
+          uint8_t* hb = Hb + size_t(ob) * kBfBox;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(hb + sw64(lane, g)) = u[g];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const long long b0 = (long long)row0 / ep.T;   // T % 32 == 0: all 32 rows share the batch element
+            tma_store_4d(which == 0 ? &tm.h : &tm.l, hb, d0, int(row0 - b0 * ep.T), h, int(b0));
+            bulk_commit();
+          }
+          ++n_out;
+          continue;
+        }
+
+        // ---- row-major outputs: out = resid + alpha * x
+        if (ep.has_resid) {
+          const int slot = int(n_cons % uint32_t(ep.nr));
+          mbar_wait(&rfull[slot], (n_cons / uint32_t(ep.nr)) & 1);
+          const uint8_t* rb = Rb + size_t(slot) * kF32Box;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128(lane, g));
+            v[g * 4 + 0] = fmaf(ep.alpha, v[g * 4 + 0], r4.x);
+            v[g * 4 + 1] = fmaf(ep.alpha, v[g * 4 + 1], r4.y);
+            v[g * 4 + 2] = fmaf(ep.alpha, v[g * 4 + 2], r4.z);
+            v[g * 4 + 3] = fmaf(ep.alpha, v[g * 4 + 3], r4.w);
+          }
+          ++n_cons;
+          __syncwarp();                              // every lane has its residual values: the slot can be refilled
+          if (lane == 0) prefetch_resid();
+        } else if (ep.alpha != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+        }
+        if (!any_store) continue;
+        const int ob = (ep.nob == 2) ? int(n_out & 1) : 0;
+        if (lane == 0) { if (ep.nob == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+        __syncwarp();
+        uint8_t* fb = Ob + size_t(ob) * kF32Box;
+        uint8_t* hb = Hb + size_t(ob) * kBfBox;
+        uint8_t* lb = Lb + size_t(ob) * kBfBox;
+        if (ep.has_f32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(fb + sw128(lane, g)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+        if (ep.has_hi) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float a = v[g * 8 + 2 * q], b = v[g * 8 + 2 * q + 1];
+              const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+              hi[q] = pack_bf16x2(ah, bh);
+              lo[q] = pack_bf16x2(a - ah, b - bh);
+            }
+            *reinterpret_cast<uint4*>(hb + sw64(lane, g)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (ep.has_lo) *reinterpret_cast<uint4*>(lb + sw64(lane, g)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (ep.has_f32) {
+            if (col0 < ep.split_col) tma_store_2d(&tm.o0, fb, col0, row0);
+            else tma_store_2d(&tm.o1, fb, col0 - ep.split_col, row0);
+          }
+          if (ep.has_hi) tma_store_2d(&tm.h, hb, col0, row0);
+          if (ep.has_lo) tma_store_2d(&tm.l, lb, col0, row0);
+          bulk_commit();
+        }
+        ++n_out;
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
     }
+    if (lane == 0) bulk_wait_all<0>();     // smem boxes must outlive their stores
   }
 
   tc_fence_before();
@@ -175,26 +379,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 template <int BN>
 int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
+  TcEpi e;
+  e.mode = ep.mode; e.bias = ep.bias; e.act = ep.act; e.alpha = ep.alpha; e.split_col = ep.split_col;
+  TcMaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (ep.mode == EPI_ROWMAJOR) {
+    e.has_resid = ep.resid != nullptr;
+    e.has_f32 = ep.out_f32 != nullptr;
+    e.has_hi = ep.out_hi != nullptr;
+    e.has_lo = ep.out_hi != nullptr && ep.out_lo != nullptr;
+    IEF_CHECK(ep.split_col % CW == 0 || ep.split_col >= g.N, "gemm_tc: split_col must be a multiple of %d", CW);
+    IEF_CHECK(!e.has_f32 || (ep.ld_f32 % 4 == 0), "gemm_tc: ld_f32 must be a multiple of 4");
+    IEF_CHECK(!e.has_hi || (ep.ld_bf % 8 == 0), "gemm_tc: ld_bf must be a multiple of 8");
+    IEF_CHECK(!e.has_resid || (ep.ld_resid % 4 == 0), "gemm_tc: ld_resid must be a multiple of 4");
+  } else if (ep.mode == EPI_QKV) {
+    IEF_CHECK(ep.q && ep.k && ep.vt, "gemm_tc: QKV epilogue needs q, k and vt");
+    IEF_CHECK(ep.D % CW == 0 && ep.dh % CW == 0 && g.N == 3 * ep.D && ep.T > 0,
+              "gemm_tc: QKV epilogue needs D %% 32 == 0, dh %% 32 == 0, N == 3D");
+    e.q = ep.q; e.k = ep.k; e.vt = ep.vt; e.T = ep.T; e.H = ep.H; e.dh = ep.dh; e.dhp = ep.dhp; e.Tpad = ep.Tpad;
+    e.D = ep.D; e.qscale = ep.qscale;
+    e.qk_tma = (ep.T % 32 == 0) ? 1 : 0;
+    e.has_hi = e.qk_tma;
+  }
+  // per-warp epilogue smem: a residual ring (3 boxes) when there is a residual, output boxes ping-pong when they fit
+  e.nr = e.has_resid ? 3 : 0;
+  const uint32_t out_bytes = (e.has_f32 ? kF32Box : 0) + (e.has_hi ? kBfBox : 0) + (e.has_lo ? kBfBox : 0);
+  e.nob = (e.nr * kF32Box + 2 * out_bytes <= 16384) ? 2 : 1;
+  e.warp_bytes = e.nr * kF32Box + e.nob * out_bytes;
+  const uint32_t fixed = 1024 + 4 * e.warp_bytes + kBarBytes;
+  int stages = int((kSmemLimit - fixed) / Cfg::kStageBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (g.force_stages > 0 && g.force_stages < stages) stages = g.force_stages;
+  IEF_CHECK(stages >= 2, "gemm_tc: no room for a 2-stage operand ring (BN=%d)", BN);
+  e.stages = stages;
+  const size_t smem_bytes = fixed + size_t(stages) * Cfg::kStageBytes;
+
   static bool attr_set = false;
   if (!attr_set) {
-    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(Cfg::kSmemBytes)));
+    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)));
     attr_set = true;
   }
-  CUtensorMap a0, a1, b0, b1;
-  IEF_TRY(make_tmap_2d(&a0, g.A_hi, g.K, g.M, uint64_t(g.lda) * 2, BK, BM));
-  IEF_TRY(make_tmap_2d(&b0, g.W_hi, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN));
+  IEF_TRY(make_tmap_2d(&tm.a0, g.A_hi, g.K, g.M, uint64_t(g.lda) * 2, BK, BM));
+  IEF_TRY(make_tmap_2d(&tm.b0, g.W_hi, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN));
   if (g.nsplit == 3) {
-    IEF_TRY(make_tmap_2d(&a1, g.A_lo, g.K, g.M, uint64_t(g.lda) * 2, BK, BM));
-    IEF_TRY(make_tmap_2d(&b1, g.W_lo, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN));
+    IEF_TRY(make_tmap_2d(&tm.a1, g.A_lo, g.K, g.M, uint64_t(g.lda) * 2, BK, BM));
+    IEF_TRY(make_tmap_2d(&tm.b1, g.W_lo, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN));
   } else {
-    a1 = a0;
-    b1 = b0;
+    tm.a1 = tm.a0;
+    tm.b1 = tm.b0;
+  }
+  if (e.has_resid)
+    IEF_TRY(make_tmap_2d(&tm.r, ep.resid, g.N, g.M, uint64_t(ep.ld_resid) * 4, CW, 32, TM_F32, TM_SWIZZLE_128B));
+  if (e.has_f32) {
+    const uint64_t w0 = ep.split_col < g.N ? ep.split_col : g.N;
+    IEF_TRY(make_tmap_2d(&tm.o0, ep.out_f32, w0, g.M, uint64_t(ep.ld_f32) * 4, CW, 32, TM_F32, TM_SWIZZLE_128B));
+    if (ep.split_col < g.N) {
+      IEF_CHECK(ep.out_f32_b != nullptr, "gemm_tc: split_col set without out_f32_b");
+      IEF_TRY(make_tmap_2d(&tm.o1, ep.out_f32_b, g.N - ep.split_col, g.M, uint64_t(ep.ld_f32) * 4, CW, 32, TM_F32,
+                           TM_SWIZZLE_128B));
+    }
+  }
+  if (ep.mode == EPI_ROWMAJOR && e.has_hi) {
+    IEF_TRY(make_tmap_2d(&tm.h, ep.out_hi, g.N, g.M, uint64_t(ep.ld_bf) * 2, CW, 32, TM_BF16, TM_SWIZZLE_64B));
+    if (e.has_lo)
+      IEF_TRY(make_tmap_2d(&tm.l, ep.out_lo, g.N, g.M, uint64_t(ep.ld_bf) * 2, CW, 32, TM_BF16, TM_SWIZZLE_64B));
+  }
+  if (ep.mode == EPI_QKV && e.qk_tma) {
+    const uint64_t Bn = (uint64_t(g.M) + ep.T - 1) / ep.T;
+    const uint64_t dims[4] = {uint64_t(ep.dhp), uint64_t(ep.T), uint64_t(ep.H), Bn};
+    const uint64_t strides[3] = {uint64_t(ep.dhp) * 2, uint64_t(ep.T) * ep.dhp * 2, uint64_t(ep.H) * ep.T * ep.dhp * 2};
+    const uint32_t box[4] = {CW, 32, 1, 1};
+    IEF_TRY(make_tmap_4d(&tm.h, ep.q, dims, strides, box, TM_BF16, TM_SWIZZLE_64B));
+    IEF_TRY(make_tmap_4d(&tm.l, ep.k, dims, strides, box, TM_BF16, TM_SWIZZLE_64B));
   }
   const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN;
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, g.M, g.N, g.K, g.nsplit, ep);
+  gemm_tc_kernel<BN><<<grid, 192, smem_bytes, stream>>>(tm, g.M, g.N, g.K, g.nsplit, e);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

@@ -52,7 +52,7 @@ static int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuin
     set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
     return IEFVAD_ERR_CUDA;
   }
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt = (dtype == TM_F32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = (swizzle == TM_SWIZZLE_NONE) ? CU_TENSOR_MAP_SWIZZLE_NONE
                                 : (swizzle == TM_SWIZZLE_64B) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -82,6 +82,14 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, box2};
   return encode(out, base, 3, dims, strides, box, TM_BF16, TM_SWIZZLE_128B);
+}
+
+int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                 const uint32_t box[4], int dtype, int swizzle) {
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+  return encode(out, base, 4, d, s, b, dtype, swizzle);
 }
 
 }  // namespace iefvad

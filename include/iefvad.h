@@ -151,10 +151,11 @@ int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, co
  * ---------------------------------------------------------------------------------------------- */
 
 /* Micro-benchmark of the tcgen05 GEMM on library-allocated buffers (synchronises; default stream): M x N x K,
- * nsplit 1 | 3, tile_n 0 | 64 | 128 | 256, epi_kind 0 = mainloop only (discard), 1 = fp32 out, 2 = refinement
+ * nsplit 1 | 3, tile_n 0 | 64 | 128 | 256, stages 0 (= as many as fit) or a cap on the operand ring depth, epi_kind 0 = mainloop only (discard), 1 = fp32 out, 2 = refinement
  * epilogue (fp32 residual in, fp32 + bf16 hi/lo out), 3 = ReLU -> bf16 hi/lo, 4 = QKV scatter.  Writes the mean
  * device time of `iters` back-to-back launches (CUDA events). */
-int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int epi_kind, int iters, float* ms_per_iter);
+int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,
+                      float* ms_per_iter);
 
 /* number of CUDA kernels this library has launched since load (process-wide) */
 uint64_t iefvad_launch_count(void);
