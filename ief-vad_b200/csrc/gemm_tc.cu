@@ -52,7 +52,7 @@ struct TcEpi {
   int has_resid = 0, has_f32 = 0, has_hi = 0, has_lo = 0;
   int split_col = 1 << 30;
   int nr = 0;              // residual ring depth (per warp)
-  int nob = 1;             // output boxes per kind (1 = wait for the previous store before refilling, 2 = ping-pong)
+  int inplace = 0;         // the fp32 output is written over the residual box it was computed from (ring slot)
   uint32_t warp_bytes = 0; // per-warp epilogue smem
   int stages = 4;
   // EPI_QKV
@@ -84,7 +84,10 @@ struct TcCfg {
 __device__ __forceinline__ uint32_t sw128(int row, int g) { return uint32_t(row) * 128u + (uint32_t(g ^ (row & 7)) << 4); }
 __device__ __forceinline__ uint32_t sw64(int row, int g) { return uint32_t(row) * 64u + (uint32_t(g ^ ((row >> 1) & 3)) << 4); }
 
-template <int BN>
+// MODE (EPI_ROWMAJOR / EPI_QKV) and ACT are compile-time so that each instance carries only the epilogue code it
+// runs: the epilogue warps execute long straight-line chunk bodies and a kernel with every variant inlined
+// spent most of its epilogue time in instruction-cache misses (ncu: stall_no_inst).
+template <int BN, int MODE, int ACT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nsplit, const TcEpi ep) {
   using Cfg = TcCfg<BN>;
@@ -187,15 +190,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;         // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     uint8_t* wb = epi_base + size_t(warp - 2) * ep.warp_bytes;
-    uint8_t* Rb = wb;                                              // [nr] fp32 residual boxes
-    uint8_t* Ob = Rb + size_t(ep.nr) * kF32Box;                    // [nob] fp32 output boxes
-    uint8_t* Hb = Ob + (ep.has_f32 ? size_t(ep.nob) * kF32Box : 0);  // [nob] bf16 hi (or q / k) boxes
-    uint8_t* Lb = Hb + (ep.has_hi ? size_t(ep.nob) * kBfBox : 0);    // [nob] bf16 lo boxes
+    uint8_t* Rb = wb;                                                      // [nr] fp32 residual (/ in-place output) boxes
+    uint8_t* Ob = Rb + size_t(ep.nr) * kF32Box;                            // [2] fp32 output boxes (no residual ring)
+    uint8_t* Hb = Ob + ((ep.has_f32 && !ep.inplace) ? 2 * kF32Box : 0);    // [2] bf16 hi (or q / k) boxes
+    uint8_t* Lb = Hb + (ep.has_hi ? 2 * kBfBox : 0);                       // [2] bf16 lo boxes
     uint64_t* rfull = rfull_all + (warp - 2) * kMaxResidSlots;
     const bool discard = ep.mode == EPI_DISCARD;
-    const bool any_store = !discard && (ep.has_f32 || ep.has_hi);
 
-    // residual prefetch cursor (lane 0): walks the same (tile, chunk) sequence as the consumer, nr chunks ahead
+    // residual prefetch cursor (lane 0): walks the same (tile, chunk) sequence as the consumer, ahead of it
     int pf_tile = blockIdx.x, pf_c = 0;
     uint32_t pf_n = 0;
     auto chunks_of = [&](int tile) {
@@ -217,152 +219,182 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       for (int i = 0; i < ep.nr; ++i) prefetch_resid();
     }
     uint32_t n_cons = 0;       // residual chunks consumed
-    uint32_t n_out = 0;        // output chunks produced
+    uint32_t n_out = 0;        // output chunks handed to TMA (one bulk group each)
 
+    // bias of the next chunk, fetched one chunk ahead (8 x 16-byte broadcast loads per thread)
+    float4 bnext[8];
+    auto fetch_bias = [&](int col0) {
+      if (ep.bias == nullptr) return;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) bnext[g] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + g);
+    };
+
+    // Output discipline: chunk n writes boxes [n & 1] (or its in-place residual slot).  After committing the
+    // stores of chunk n lane 0 waits until every group but the newest has finished READING smem, so when the warp
+    // meets again at the top of the next store phase the boxes of chunk n - 1 are free.
+    auto finish_chunk = [&]() {      // lane 0, after issuing the stores of one chunk
+      bulk_commit();
+      bulk_wait_read<1>();
+      if (ep.inplace && n_out > 0) prefetch_resid();     // the slot of the previous chunk is free again
+    };
+
+    int tile = blockIdx.x;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      const int nchunks = chunks_of(tile);
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
-      const int row0 = m_blk * BM + quarter * 32;     // first row of this warp; this thread owns row0 + lane
-      const uint32_t t0 = tmem_base + uint32_t(as * BN) + (uint32_t(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        float v[32];
-        tmem_ld32(t0 + uint32_t(c * CW), v);
-        tmem_ld_wait();
-        if (c == nchunks - 1) {           // accumulator fully in registers: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
-        }
-        if (discard) continue;
-        const int col0 = n_blk * BN + c * CW;
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (ep.act != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-        }
+    int m_blk = 0, n_blk = 0, row0 = 0, nchunks = 0;
 
-        if (ep.mode == EPI_QKV) {
-          const int which = col0 / ep.D;                 // 0 = q, 1 = k, 2 = v (a chunk never straddles: D % 32 == 0)
-          const int cc = col0 - which * ep.D;
-          const int h = cc / ep.dh;                      // dh % 32 == 0 -> a chunk stays inside one head
-          const int d0 = cc - h * ep.dh;
-          const long long row = (long long)row0 + lane;
-          const long long b = row / ep.T;
-          const int t = int(row - b * ep.T);
-          if (which == 2) {
-            // V^T [B, H, dh, Tpad]: consecutive lanes = consecutive t, so each of the 32 stores is one 64-byte run
-            if (row < M) {
-              bf16* dst = ep.vt + ((b * ep.H + h) * ep.dh + d0) * (long long)ep.Tpad + t;
+    auto process = [&](float (&v)[32], int c) {
+      const int col0 = n_blk * BN + c * CW;
+      if (ep.bias) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dst[(long long)j * ep.Tpad] = __float2bfloat16_rn(v[j]);
-            }
-            continue;
-          }
-          const float s = (which == 0) ? ep.qscale : 1.f;
-          uint4 u[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            u[g].x = pack_bf16x2(v[g * 8 + 0] * s, v[g * 8 + 1] * s);
-            u[g].y = pack_bf16x2(v[g * 8 + 2] * s, v[g * 8 + 3] * s);
-            u[g].z = pack_bf16x2(v[g * 8 + 4] * s, v[g * 8 + 5] * s);
-            u[g].w = pack_bf16x2(v[g * 8 + 6] * s, v[g * 8 + 7] * s);
-          }
-          if (!ep.qk_tma) {
-            if (row < M) {
-              bf16* dst = (which == 0 ? ep.q : ep.k) + ((b * ep.H + h) * ep.T + t) * (long long)ep.dhp + d0;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + g * 8) = u[g];
-            }
-            continue;
-          }
-          const int ob = (ep.nob == 2) ? int(n_out & 1) : 0;
-          if (lane == 0) { if (ep.nob == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-          __syncwarp();
-          uint8_t* hb = Hb + size_t(ob) * kBfBox;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(hb + sw64(lane, g)) = u[g];
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            const long long b0 = (long long)row0 / ep.T;   // T % 32 == 0: all 32 rows share the batch element
-            tma_store_4d(which == 0 ? &tm.h : &tm.l, hb, d0, int(row0 - b0 * ep.T), h, int(b0));
-            bulk_commit();
-          }
-          ++n_out;
-          continue;
+        for (int g = 0; g < 8; ++g) {
+          v[g * 4 + 0] += bnext[g].x; v[g * 4 + 1] += bnext[g].y; v[g * 4 + 2] += bnext[g].z; v[g * 4 + 3] += bnext[g].w;
         }
+        if (c + 1 < nchunks) fetch_bias(col0 + CW);
+      }
+      if (ACT != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ACT);
+      }
 
-        // ---- row-major outputs: out = resid + alpha * x
-        if (ep.has_resid) {
-          const int slot = int(n_cons % uint32_t(ep.nr));
-          mbar_wait(&rfull[slot], (n_cons / uint32_t(ep.nr)) & 1);
-          const uint8_t* rb = Rb + size_t(slot) * kF32Box;
+      if (MODE == EPI_QKV) {
+        const int which = col0 / ep.D;                 // 0 = q, 1 = k, 2 = v (a chunk never straddles: D % 32 == 0)
+        const int cc = col0 - which * ep.D;
+        const int h = cc / ep.dh;                      // dh % 32 == 0 -> a chunk stays inside one head
+        const int d0 = cc - h * ep.dh;
+        const long long row = (long long)row0 + lane;
+        const long long b = row / ep.T;
+        const int t = int(row - b * ep.T);
+        if (which == 2) {
+          // V^T [B, H, dh, Tpad]: consecutive lanes = consecutive t, so each of the 32 stores is one 64-byte run
+          if (row < M) {
+            bf16* dst = ep.vt + ((b * ep.H + h) * ep.dh + d0) * (long long)ep.Tpad + t;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128(lane, g));
-            v[g * 4 + 0] = fmaf(ep.alpha, v[g * 4 + 0], r4.x);
-            v[g * 4 + 1] = fmaf(ep.alpha, v[g * 4 + 1], r4.y);
-            v[g * 4 + 2] = fmaf(ep.alpha, v[g * 4 + 2], r4.z);
-            v[g * 4 + 3] = fmaf(ep.alpha, v[g * 4 + 3], r4.w);
+            for (int j = 0; j < 32; ++j) dst[(long long)j * ep.Tpad] = __float2bfloat16_rn(v[j]);
           }
-          ++n_cons;
-          __syncwarp();                              // every lane has its residual values: the slot can be refilled
-          if (lane == 0) prefetch_resid();
-        } else if (ep.alpha != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+          return;
         }
-        if (!any_store) continue;
-        const int ob = (ep.nob == 2) ? int(n_out & 1) : 0;
-        if (lane == 0) { if (ep.nob == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-        __syncwarp();
-        uint8_t* fb = Ob + size_t(ob) * kF32Box;
-        uint8_t* hb = Hb + size_t(ob) * kBfBox;
-        uint8_t* lb = Lb + size_t(ob) * kBfBox;
-        if (ep.has_f32) {
+        const float s = (which == 0) ? ep.qscale : 1.f;
+        uint4 u[4];
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(fb + sw128(lane, g)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        for (int g = 0; g < 4; ++g) {
+          u[g].x = pack_bf16x2(v[g * 8 + 0] * s, v[g * 8 + 1] * s);
+          u[g].y = pack_bf16x2(v[g * 8 + 2] * s, v[g * 8 + 3] * s);
+          u[g].z = pack_bf16x2(v[g * 8 + 4] * s, v[g * 8 + 5] * s);
+          u[g].w = pack_bf16x2(v[g * 8 + 6] * s, v[g * 8 + 7] * s);
         }
-        if (ep.has_hi) {
+        if (!ep.qk_tma) {
+          if (row < M) {
+            bf16* dst = (which == 0 ? ep.q : ep.k) + ((b * ep.H + h) * ep.T + t) * (long long)ep.dhp + d0;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float a = v[g * 8 + 2 * q], b = v[g * 8 + 2 * q + 1];
-              const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
-              hi[q] = pack_bf16x2(ah, bh);
-              lo[q] = pack_bf16x2(a - ah, b - bh);
-            }
-            *reinterpret_cast<uint4*>(hb + sw64(lane, g)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (ep.has_lo) *reinterpret_cast<uint4*>(lb + sw64(lane, g)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + g * 8) = u[g];
           }
+          return;
         }
+        uint8_t* hb = Hb + size_t(n_out & 1) * kBfBox;
+        __syncwarp();                                  // lane 0 is back from bulk_wait_read: box [n_out & 1] is free
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(hb + sw64(lane, g)) = u[g];
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (ep.has_f32) {
-            if (col0 < ep.split_col) tma_store_2d(&tm.o0, fb, col0, row0);
-            else tma_store_2d(&tm.o1, fb, col0 - ep.split_col, row0);
-          }
-          if (ep.has_hi) tma_store_2d(&tm.h, hb, col0, row0);
-          if (ep.has_lo) tma_store_2d(&tm.l, lb, col0, row0);
-          bulk_commit();
+          const long long b0 = (long long)row0 / ep.T;   // T % 32 == 0: all 32 rows share the batch element
+          tma_store_4d(which == 0 ? &tm.h : &tm.l, hb, d0, int(row0 - b0 * ep.T), h, int(b0));
+          finish_chunk();
         }
         ++n_out;
+        return;
+      }
+
+      // ---- row-major outputs: out = resid + alpha * x
+      uint8_t* fb = Ob + size_t(n_out & 1) * kF32Box;
+      if (ep.has_resid) {
+        const int slot = int(n_cons % uint32_t(ep.nr));
+        mbar_wait(&rfull[slot], (n_cons / uint32_t(ep.nr)) & 1);
+        uint8_t* rb = Rb + size_t(slot) * kF32Box;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128(lane, g));
+          v[g * 4 + 0] = fmaf(ep.alpha, v[g * 4 + 0], r4.x);
+          v[g * 4 + 1] = fmaf(ep.alpha, v[g * 4 + 1], r4.y);
+          v[g * 4 + 2] = fmaf(ep.alpha, v[g * 4 + 2], r4.z);
+          v[g * 4 + 3] = fmaf(ep.alpha, v[g * 4 + 3], r4.w);
+        }
+        ++n_cons;
+        if (ep.inplace) {
+          fb = rb;                                     // every lane overwrites exactly the 128 bytes it just read
+        } else {
+          __syncwarp();                                // every lane has its residual values: refill the slot
+          if (lane == 0) prefetch_resid();
+        }
+      } else if (ep.alpha != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+      }
+      if (!(ep.has_f32 || ep.has_hi)) return;
+      uint8_t* hb = Hb + size_t(n_out & 1) * kBfBox;
+      uint8_t* lb = Lb + size_t(n_out & 1) * kBfBox;
+      __syncwarp();                                    // lane 0 is back from bulk_wait_read: boxes [n_out & 1] are free
+      if (ep.has_f32) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(fb + sw128(lane, g)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+      if (ep.has_hi) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = v[g * 8 + 2 * q], b = v[g * 8 + 2 * q + 1];
+            const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+            hi[q] = pack_bf16x2(ah, bh);
+            lo[q] = pack_bf16x2(a - ah, b - bh);
+          }
+          *reinterpret_cast<uint4*>(hb + sw64(lane, g)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (ep.has_lo) *reinterpret_cast<uint4*>(lb + sw64(lane, g)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (ep.has_f32) {
+          if (col0 < ep.split_col) tma_store_2d(&tm.o0, fb, col0, row0);
+          else tma_store_2d(&tm.o1, fb, col0 - ep.split_col, row0);
+        }
+        if (ep.has_hi) tma_store_2d(&tm.h, hb, col0, row0);
+        if (ep.has_lo) tma_store_2d(&tm.l, lb, col0, row0);
+        finish_chunk();
+      }
+      ++n_out;
+    };
+
+    for (; tile < num_tiles; tile += gridDim.x, ++it) {
+      m_blk = tile / num_n;
+      n_blk = tile % num_n;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      nchunks = chunks_of(tile);
+      row0 = m_blk * BM + quarter * 32;               // first row of this warp; this thread owns row0 + lane
+      if (!discard) fetch_bias(n_blk * BN);           // in flight while the accumulator is still being produced
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + uint32_t(as * BN) + (uint32_t(quarter * 32) << 16);
+      auto release_tmem = [&]() {                     // accumulator fully in registers: hand the buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+      };
+      // the tcgen05.ld of chunk c + 1 is in flight (into vn) while chunk c is processed (in v)
+      float v[32], vn[32];
+      tmem_ld32(t0, vn);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        tmem_ld_wait_for(vn);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = vn[j];
+        if (c + 1 < nchunks) tmem_ld32(t0 + uint32_t((c + 1) * CW), vn);
+        else release_tmem();
+        if (!discard) process(v, c);
       }
     }
     if (lane == 0) bulk_wait_all<0>();     // smem boxes must outlive their stores
@@ -374,6 +406,20 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BN, int MODE, int ACT>
+int launch_inst(const TcMaps& tm, const GemmTcArgs& g, const TcEpi& e, int grid, size_t smem_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(kSmemLimit)));
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN, MODE, ACT><<<grid, 192, smem_bytes, stream>>>(tm, g.M, g.N, g.K, g.nsplit, e);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
 }
 
 template <int BN>
@@ -401,11 +447,12 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
     e.qk_tma = (ep.T % 32 == 0) ? 1 : 0;
     e.has_hi = e.qk_tma;
   }
-  // per-warp epilogue smem: a residual ring (3 boxes) when there is a residual, output boxes ping-pong when they fit
-  e.nr = e.has_resid ? 3 : 0;
-  const uint32_t out_bytes = (e.has_f32 ? kF32Box : 0) + (e.has_hi ? kBfBox : 0) + (e.has_lo ? kBfBox : 0);
-  e.nob = (e.nr * kF32Box + 2 * out_bytes <= 16384) ? 2 : 1;
-  e.warp_bytes = e.nr * kF32Box + e.nob * out_bytes;
+  // per-warp epilogue smem: a residual ring whose slots double as the fp32 output boxes (in place), else two fp32
+  // output boxes; bf16 boxes always ping-pong
+  e.inplace = (e.has_resid && e.has_f32) ? 1 : 0;
+  e.nr = e.has_resid ? ((e.has_hi && e.inplace) ? 3 : 4) : 0;
+  e.warp_bytes = e.nr * kF32Box + ((e.has_f32 && !e.inplace) ? 2 * kF32Box : 0) + (e.has_hi ? 2 * kBfBox : 0) +
+                 (e.has_lo ? 2 * kBfBox : 0);
   const uint32_t fixed = 1024 + 4 * e.warp_bytes + kBarBytes;
   int stages = int((kSmemLimit - fixed) / Cfg::kStageBytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -414,11 +461,6 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   e.stages = stages;
   const size_t smem_bytes = fixed + size_t(stages) * Cfg::kStageBytes;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)));
-    attr_set = true;
-  }
   IEF_TRY(make_tmap_2d(&tm.a0, g.A_hi, g.K, g.M, uint64_t(g.lda) * 2, BK, BM));
   IEF_TRY(make_tmap_2d(&tm.b0, g.W_hi, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN));
   if (g.nsplit == 3) {
@@ -455,10 +497,16 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN;
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN><<<grid, 192, smem_bytes, stream>>>(tm, g.M, g.N, g.K, g.nsplit, e);
-  count_launches(1);
-  IEF_CUDA(cudaGetLastError());
-  return IEFVAD_OK;
+  if (ep.mode == EPI_QKV) {
+    IEF_CHECK(ep.act == ACT_NONE, "gemm_tc: the QKV epilogue has no activation");
+    return launch_inst<BN, EPI_QKV, ACT_NONE>(tm, g, e, grid, smem_bytes, stream);
+  }
+  switch (ep.act) {       // EPI_DISCARD runs the row-major instance and drops the accumulator
+    case ACT_NONE: return launch_inst<BN, EPI_ROWMAJOR, ACT_NONE>(tm, g, e, grid, smem_bytes, stream);
+    case ACT_RELU: return launch_inst<BN, EPI_ROWMAJOR, ACT_RELU>(tm, g, e, grid, smem_bytes, stream);
+    case ACT_QUICKGELU: return launch_inst<BN, EPI_ROWMAJOR, ACT_QUICKGELU>(tm, g, e, grid, smem_bytes, stream);
+    default: set_error("gemm_tc: unknown activation %d", ep.act); return IEFVAD_ERR_INVALID;
+  }
 }
 
 }  // namespace
