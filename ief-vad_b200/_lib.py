@@ -44,6 +44,7 @@ _SIGS = {
     "iefvad_clas2": (_i, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
     "iefvad_sort_scores": (_i, [_vp, _i64, _vp, _vp]),
     "iefvad_auc_ap": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "iefvad_auc_ap_multi": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "iefvad_segment_copy": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "iefvad_bench_gemm": (_i, [_i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "iefvad_launch_count": (C.c_uint64, []),

@@ -185,7 +185,8 @@ int iefvad_linear(const float* x, const float* w, const float* bias, const float
   GemmTcArgs g;
   g.A_hi = (bf16*)xh; g.A_lo = (bf16*)xl; g.W_hi = (bf16*)wh; g.W_lo = (bf16*)wl;
   g.M = int(rows); g.N = out_f; g.K = in_f; g.lda = in_f; g.ldw = in_f; g.nsplit = plan == 1 ? 3 : 1;
-  g.force_bn = tile_n;
+  g.force_bn = tile_n == 512 ? 256 : tile_n;          // 512 = 256-column tiles on CTA pairs
+  g.force_cg = tile_n == 512 ? 2 : (tile_n ? 1 : 0);
   return gemm_tc(g, ep, sms, st);
 }
 
@@ -279,6 +280,11 @@ int iefvad_auc_ap(const float* scores, const int32_t* pos, int64_t n, int repeat
   return auc_ap(scores, pos, n, repeat, out, order, static_cast<cudaStream_t>(stream));
 }
 
+int iefvad_auc_ap_multi(const float* scores, const int32_t* pos, const uint32_t* member, int64_t n, int repeat,
+                        int num_subsets, double* out, int32_t* order, void* stream) {
+  return auc_ap_multi(scores, pos, member, n, repeat, num_subsets, out, order, static_cast<cudaStream_t>(stream));
+}
+
 int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, const int64_t* dst_off,
                         const int64_t* len, int64_t nseg, void* stream) {
   return segment_copy(src, reinterpret_cast<const long long*>(src_off), dst,
@@ -331,7 +337,9 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stage
   }
   GemmTcArgs g;
   g.A_hi = (bf16*)ah; g.A_lo = (bf16*)al; g.W_hi = (bf16*)wh; g.W_lo = (bf16*)wl;
-  g.M = int(M); g.N = N; g.K = K; g.lda = K; g.ldw = K; g.nsplit = nsplit; g.force_bn = tile_n; g.force_stages = stages;
+  g.M = int(M); g.N = N; g.K = K; g.lda = K; g.ldw = K; g.nsplit = nsplit; g.force_stages = stages;
+  g.force_bn = tile_n == 512 ? 256 : tile_n;
+  g.force_cg = tile_n == 512 ? 2 : (tile_n ? 1 : 0);
   for (int i = 0; i < 3; ++i) IEF_TRY(gemm_tc(g, ep, sms, st));
   cudaEvent_t e0, e1;
   IEF_CUDA(cudaEventCreate(&e0));

@@ -15,6 +15,7 @@ struct GemmTcArgs {
   int nsplit = 1;              // 1: plain bf16;  3: hi.hi + hi.lo + lo.hi
   int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256 (tests, tuning)
   int force_stages = 0;        // 0 = as many smem stages as fit beside the epilogue buffers (tuning)
+  int force_cg = 0;            // 0 = heuristic, 1 = one CTA per tile, 2 = CTA pair (cta_group::2, 256-row tiles)
 };
 
 // C = epilogue(A . W^T): bf16 operands through TMA, tcgen05.mma into TMEM, and an epilogue whose global traffic

@@ -71,10 +71,10 @@ struct TcMaps {
   CUtensorMap h, l;             // bf16 hi / lo outputs; in EPI_QKV: q / k as 4-D {d, t, head, batch}
 };
 
-template <int BN>
+template <int BN, int CG = 1>
 struct TcCfg {
   static constexpr uint32_t kABytes = BM * BK * 2;
-  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kBBytes = (BN / CG) * BK * 2;    // a CTA pair splits the W tile: each CTA loads BN/2 rows
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
@@ -87,10 +87,17 @@ __device__ __forceinline__ uint32_t sw64(int row, int g) { return uint32_t(row) 
 // MODE (EPI_ROWMAJOR / EPI_QKV) and ACT are compile-time so that each instance carries only the epilogue code it
 // runs: the epilogue warps execute long straight-line chunk bodies and a kernel with every variant inlined
 // spent most of its epilogue time in instruction-cache misses (ncu: stall_no_inst).
-template <int BN, int MODE, int ACT>
+//
+// CG == 2 runs the same roles on a CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each
+// CTA owning 128 rows of A / of the accumulator and HALF of the W tile, which the tensor cores of both SMs share.
+// That cuts the smem fill + operand-read traffic per flop by a third - the resource the 1-CTA kernel saturates
+// (mainloop ~80 % of the tensor rate, and every epilogue byte staged through smem slows it further).  Only the
+// leader CTA issues MMAs; its commits multicast to the mbarriers of both CTAs; both producers signal the leader's
+// `full` barrier; both epilogues arrive on the leader's `tempty`.
+template <int BN, int MODE, int ACT, int CG>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nsplit, const TcEpi ep) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = ep.stages;
@@ -105,9 +112,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // rank in the CTA pair; 0 = leader
+  const int num_m = (M + BM * CG - 1) / (BM * CG);               // tiles of BM * CG rows (one per CTA / pair)
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   const int kb_per_seg = K / BK;
   const int total_kb = kb_per_seg * nsplit;
 
@@ -124,17 +133,22 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], 4 * CG);       // the epilogue warps of every CTA of the pair arrive on the leader's
     }
     for (int s = 0; s < 4 * kMaxResidSlots; ++s) mbar_init(&rfull_all[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -143,29 +157,37 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = (tile / num_n) * CG + int(rank), n_blk = tile % num_n;
         for (int kb = 0; kb < total_kb; ++kb) {
           const int seg = kb / kb_per_seg, kk = kb - seg * kb_per_seg;
           const CUtensorMap* ma = (seg == 2) ? &tm.a1 : &tm.a0;   // hi.hi, hi.lo, lo.hi
           const CUtensorMap* mb = (seg == 1) ? &tm.b1 : &tm.b0;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + size_t(s) * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-          tma_load_2d(ma, &full[s], sa, kk * BK, m_blk * BM);
-          tma_load_2d(mb, &full[s], sa + Cfg::kABytes, kk * BK, n_blk * BN);
+          if (CG == 2) {
+            // both CTAs' boxes complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
+            tma_load_2d_cg2(ma, lead_full, sa, kk * BK, m_blk * BM);
+            tma_load_2d_cg2(mb, lead_full, sa + Cfg::kABytes, kk * BK, n_blk * BN + int(rank) * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+            tma_load_2d(ma, &full[s], sa, kk * BK, m_blk * BM);
+            tma_load_2d(mb, &full[s], sa + Cfg::kABytes, kk * BK, n_blk * BN);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
@@ -178,12 +200,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4)
-            umma_bf16(d_tmem, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
-          tc_commit(&empty[s]);           // smem slot reusable once these MMAs retire
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            if (CG == 2) umma_bf16_cg2(d_tmem, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          if (CG == 2) tc_commit_cg2(&empty[s], 3); else tc_commit(&empty[s]);   // smem slot reusable once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(&tfull[as]);            // accumulator complete
+        if (CG == 2) tc_commit_cg2(&tfull[as], 3); else tc_commit(&tfull[as]);   // accumulator complete (both CTAs)
       }
     }
   } else {
@@ -198,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     const bool discard = ep.mode == EPI_DISCARD;
 
     // residual prefetch cursor (lane 0): walks the same (tile, chunk) sequence as the consumer, ahead of it
-    int pf_tile = blockIdx.x, pf_c = 0;
+    int pf_tile = tile0, pf_c = 0;
     uint32_t pf_n = 0;
     auto chunks_of = [&](int tile) {
       const int n_blk = tile % num_n;
@@ -207,12 +231,12 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     };
     auto prefetch_resid = [&]() {
       if (pf_tile >= num_tiles) return;
-      const int m_blk = pf_tile / num_n, n_blk = pf_tile % num_n;
+      const int m_blk = (pf_tile / num_n) * CG + int(rank), n_blk = pf_tile % num_n;
       const int slot = int(pf_n % uint32_t(ep.nr));
       mbar_arrive_expect_tx(&rfull[slot], kF32Box);
       tma_load_2d(&tm.r, &rfull[slot], Rb + size_t(slot) * kF32Box, n_blk * BN + pf_c * CW, m_blk * BM + quarter * 32);
       ++pf_n;
-      if (++pf_c == chunks_of(pf_tile)) { pf_c = 0; pf_tile += gridDim.x; }
+      if (++pf_c == chunks_of(pf_tile)) { pf_c = 0; pf_tile += tile_step; }
     };
     if (ep.has_resid && lane == 0) {
       tma_prefetch_desc(&tm.r);
@@ -238,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       if (ep.inplace && n_out > 0) prefetch_resid();     // the slot of the previous chunk is free again
     };
 
-    int tile = blockIdx.x;
+    int tile = tile0;
     int it = 0;
     int m_blk = 0, n_blk = 0, row0 = 0, nchunks = 0;
 
@@ -368,8 +392,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       ++n_out;
     };
 
-    for (; tile < num_tiles; tile += gridDim.x, ++it) {
-      m_blk = tile / num_n;
+    for (; tile < num_tiles; tile += tile_step, ++it) {
+      m_blk = (tile / num_n) * CG + int(rank);
       n_blk = tile % num_n;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
@@ -382,7 +406,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       auto release_tmem = [&]() {                     // accumulator fully in registers: hand the buffer back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[as]), 0));
+          else mbar_arrive(&tempty[as]);
+        }
       };
       // the tcgen05.ld of chunk c + 1 is in flight (into vn) while chunk c is processed (in v)
       float v[32], vn[32];
@@ -401,30 +428,43 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal barriers / read TMEM of this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int MODE, int ACT>
+template <int BN, int MODE, int ACT, int CG>
 int launch_inst(const TcMaps& tm, const GemmTcArgs& g, const TcEpi& e, int grid, size_t smem_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, ACT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   int(kSmemLimit)));
     attr_set = true;
   }
-  gemm_tc_kernel<BN, MODE, ACT><<<grid, 192, smem_bytes, stream>>>(tm, g.M, g.N, g.K, g.nsplit, e);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IEF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, ACT, CG>, tm, g.M, g.N, g.K, g.nsplit, e));
   count_launches(1);
-  IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_t stream) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
   TcEpi e;
   e.mode = ep.mode; e.bias = ep.bias; e.act = ep.act; e.alpha = ep.alpha; e.split_col = ep.split_col;
   TcMaps tm;
@@ -462,10 +502,10 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   const size_t smem_bytes = fixed + size_t(stages) * Cfg::kStageBytes;
 
   IEF_TRY(make_tmap_2d(&tm.a0, g.A_hi, g.K, g.M, uint64_t(g.lda) * 2, BK, BM));
-  IEF_TRY(make_tmap_2d(&tm.b0, g.W_hi, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN));
+  IEF_TRY(make_tmap_2d(&tm.b0, g.W_hi, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN / CG));
   if (g.nsplit == 3) {
     IEF_TRY(make_tmap_2d(&tm.a1, g.A_lo, g.K, g.M, uint64_t(g.lda) * 2, BK, BM));
-    IEF_TRY(make_tmap_2d(&tm.b1, g.W_lo, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN));
+    IEF_TRY(make_tmap_2d(&tm.b1, g.W_lo, g.K, g.N, uint64_t(g.ldw) * 2, BK, BN / CG));
   } else {
     tm.a1 = tm.a0;
     tm.b1 = tm.b0;
@@ -494,17 +534,18 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
     IEF_TRY(make_tmap_4d(&tm.h, ep.q, dims, strides, box, TM_BF16, TM_SWIZZLE_64B));
     IEF_TRY(make_tmap_4d(&tm.l, ep.k, dims, strides, box, TM_BF16, TM_SWIZZLE_64B));
   }
-  const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN;
-  const int tiles = num_m * num_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int num_m = (g.M + BM * CG - 1) / (BM * CG), num_n = (g.N + BN - 1) / BN;
+  const int tiles = num_m * num_n;                       // one per CTA (CG == 1) or per CTA pair (CG == 2)
+  const int max_groups = num_sms / CG;
+  const int grid = (tiles < max_groups ? tiles : max_groups) * CG;
   if (ep.mode == EPI_QKV) {
     IEF_CHECK(ep.act == ACT_NONE, "gemm_tc: the QKV epilogue has no activation");
-    return launch_inst<BN, EPI_QKV, ACT_NONE>(tm, g, e, grid, smem_bytes, stream);
+    return launch_inst<BN, EPI_QKV, ACT_NONE, CG>(tm, g, e, grid, smem_bytes, stream);
   }
   switch (ep.act) {       // EPI_DISCARD runs the row-major instance and drops the accumulator
-    case ACT_NONE: return launch_inst<BN, EPI_ROWMAJOR, ACT_NONE>(tm, g, e, grid, smem_bytes, stream);
-    case ACT_RELU: return launch_inst<BN, EPI_ROWMAJOR, ACT_RELU>(tm, g, e, grid, smem_bytes, stream);
-    case ACT_QUICKGELU: return launch_inst<BN, EPI_ROWMAJOR, ACT_QUICKGELU>(tm, g, e, grid, smem_bytes, stream);
+    case ACT_NONE: return launch_inst<BN, EPI_ROWMAJOR, ACT_NONE, CG>(tm, g, e, grid, smem_bytes, stream);
+    case ACT_RELU: return launch_inst<BN, EPI_ROWMAJOR, ACT_RELU, CG>(tm, g, e, grid, smem_bytes, stream);
+    case ACT_QUICKGELU: return launch_inst<BN, EPI_ROWMAJOR, ACT_QUICKGELU, CG>(tm, g, e, grid, smem_bytes, stream);
     default: set_error("gemm_tc: unknown activation %d", ep.act); return IEFVAD_ERR_INVALID;
   }
 }
@@ -526,10 +567,15 @@ int gemm_tc(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_t 
     else if (g.N % 128 == 0 && num_m * (g.N / 128) >= num_sms) bn = 128;
     else bn = 64;
   }
+  // CTA pairs (256-row x 256-column tiles) whenever the shape allows and there is a tile for every pair
+  int cg = g.force_cg;
+  if (cg == 0) cg = (bn == 256 && ((g.M + 255) / 256) * (g.N / 256) >= num_sms / 2) ? 2 : 1;
+  IEF_CHECK(cg == 1 || (cg == 2 && bn == 256 && g.N % 256 == 0), "gemm_tc: CTA pairs need BN == 256 and N %% 256 == 0");
+  if (cg == 2) return launch_bn<256, 2>(g, ep, num_sms, stream);
   switch (bn) {
-    case 256: return launch_bn<256>(g, ep, num_sms, stream);
-    case 128: return launch_bn<128>(g, ep, num_sms, stream);
-    case 64: return launch_bn<64>(g, ep, num_sms, stream);
+    case 256: return launch_bn<256, 1>(g, ep, num_sms, stream);
+    case 128: return launch_bn<128, 1>(g, ep, num_sms, stream);
+    case 64: return launch_bn<64, 1>(g, ep, num_sms, stream);
     default: set_error("gemm_tc: unsupported BN=%d", bn); return IEFVAD_ERR_INVALID;
   }
 }

@@ -232,14 +232,21 @@ constexpr int SC_THREADS = 256;
 constexpr int SC_ITEMS = 8;
 constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
-__device__ __forceinline__ Tri load_item(const uint32_t* keys, const uint32_t* order, const int* pos, int repeat,
-                                         long long i, long long n) {
+// `member` (optional): bit s of member[j] says whether segment j belongs to subset s.  Subsets share the GLOBAL
+// ranking and the global tie groups: a segment outside the subset weighs (0, 0), and a tie group without members
+// adds nothing to either sum, so the filtered result equals ranking the subset on its own (the stable sort keeps
+// the relative order of its members) - class-wise and Ano-AUC cost one sort instead of one per class.
+__device__ __forceinline__ Tri load_item(const uint32_t* keys, const uint32_t* order, const int* pos,
+                                         const uint32_t* member, int subset, int repeat, long long i, long long n) {
   Tri t = {0, 0, 0};
   if (i < n) {
-    const int p = pos[order[i]];
-    t.p = p;
-    t.n = repeat - p;
-    t.g = (i > 0 && keys[i] != keys[i - 1]) ? 1 : 0;       // a new tie group starts here
+    const uint32_t j = order[i];
+    if (member == nullptr || ((member[j] >> subset) & 1u)) {
+      const int p = pos[j];
+      t.p = p;
+      t.n = repeat - p;
+    }
+    t.g = (i > 0 && keys[i] != keys[i - 1]) ? 1 : 0;       // a new (global) tie group starts here
   }
   return t;
 }
@@ -270,21 +277,24 @@ __device__ __forceinline__ Tri block_exclusive_scan(Tri v, Tri* total_out) {
 // pass 1: per-tile totals
 __global__ void __launch_bounds__(SC_THREADS)
 sc_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, const int* __restrict__ pos,
-                 int repeat, long long n, Tri* __restrict__ tile_sums) {
+                 const uint32_t* __restrict__ member, int repeat, long long n, Tri* __restrict__ tile_sums) {
   __shared__ Tri total;
+  const int subset = blockIdx.y;
   const long long base = (long long)blockIdx.x * SC_TILE + (long long)threadIdx.x * SC_ITEMS;
   Tri s = {0, 0, 0};
 #pragma unroll
-  for (int j = 0; j < SC_ITEMS; ++j) s = tri_add(s, load_item(keys, order, pos, repeat, base + j, n));
+  for (int j = 0; j < SC_ITEMS; ++j) s = tri_add(s, load_item(keys, order, pos, member, subset, repeat, base + j, n));
   block_exclusive_scan(s, &total);
   __syncthreads();
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+  if (threadIdx.x == 0) tile_sums[(long long)subset * gridDim.x + blockIdx.x] = total;
 }
 
 // pass 2: exclusive scan of the tile totals (single CTA, sequential over chunks of 256 tiles)
 __global__ void __launch_bounds__(SC_THREADS)
 sc_scan_tiles_kernel(Tri* __restrict__ tile_sums, int ntiles, Tri* __restrict__ grand_total) {
   __shared__ Tri carry, total;
+  tile_sums += (long long)blockIdx.x * ntiles;              // one CTA per subset
+  grand_total += blockIdx.x;
   if (threadIdx.x == 0) carry = {0, 0, 0};
   __syncthreads();
   for (int b0 = 0; b0 < ntiles; b0 += SC_THREADS) {
@@ -304,17 +314,20 @@ sc_scan_tiles_kernel(Tri* __restrict__ tile_sums, int ntiles, Tri* __restrict__ 
 // pass 3: full scan; at every tie-group end write the cumulative (TP, FP) into the compacted group arrays
 __global__ void __launch_bounds__(SC_THREADS)
 sc_apply_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, const int* __restrict__ pos,
-                int repeat, long long n, const Tri* __restrict__ tile_sums, long long* __restrict__ gtp,
-                long long* __restrict__ gfp) {
+                const uint32_t* __restrict__ member, int repeat, long long n, const Tri* __restrict__ tile_sums,
+                long long* __restrict__ gtp, long long* __restrict__ gfp) {
+  const int subset = blockIdx.y;
+  gtp += (long long)subset * n;
+  gfp += (long long)subset * n;
   const long long base = (long long)blockIdx.x * SC_TILE + (long long)threadIdx.x * SC_ITEMS;
   Tri items[SC_ITEMS];
   Tri s = {0, 0, 0};
 #pragma unroll
   for (int j = 0; j < SC_ITEMS; ++j) {
-    items[j] = load_item(keys, order, pos, repeat, base + j, n);
+    items[j] = load_item(keys, order, pos, member, subset, repeat, base + j, n);
     s = tri_add(s, items[j]);
   }
-  Tri run = tri_add(tile_sums[blockIdx.x], block_exclusive_scan(s, nullptr));
+  Tri run = tri_add(tile_sums[(long long)subset * gridDim.x + blockIdx.x], block_exclusive_scan(s, nullptr));
 #pragma unroll
   for (int j = 0; j < SC_ITEMS; ++j) {
     const long long i = base + j;
@@ -328,10 +341,17 @@ sc_apply_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
 
 // per tie group: 2 x trapezoid area (exact int64) and the AP term (float64); fixed-order block partials
 __global__ void __launch_bounds__(SC_THREADS)
-auc_terms_kernel(const long long* __restrict__ gtp, const long long* __restrict__ gfp, const Tri* __restrict__ grand,
-                 unsigned long long* __restrict__ area2_partial, double* __restrict__ ap_partial) {
+auc_terms_kernel(const long long* __restrict__ gtp, const long long* __restrict__ gfp, long long n,
+                 const Tri* __restrict__ grand, unsigned long long* __restrict__ area2_partial,
+                 double* __restrict__ ap_partial) {
   __shared__ unsigned long long ra[SC_THREADS / 32];
   __shared__ double rp[SC_THREADS / 32];
+  const int subset = blockIdx.y;
+  gtp += (long long)subset * n;
+  gfp += (long long)subset * n;
+  grand += subset;
+  area2_partial += (long long)subset * gridDim.x;
+  ap_partial += (long long)subset * gridDim.x;
   const long long G = grand->g + 1;
   const double P = double(grand->p);
   unsigned long long a = 0;
@@ -361,6 +381,10 @@ auc_terms_kernel(const long long* __restrict__ gtp, const long long* __restrict_
 __global__ void auc_final_kernel(const unsigned long long* __restrict__ area2_partial,
                                  const double* __restrict__ ap_partial, int nparts, const Tri* __restrict__ grand,
                                  double* __restrict__ out) {
+  area2_partial += (long long)blockIdx.x * nparts;          // one CTA (of one thread) per subset
+  ap_partial += (long long)blockIdx.x * nparts;
+  grand += blockIdx.x;
+  out += 4 * blockIdx.x;
   unsigned long long a = 0;
   double ap = 0.0;
   for (int i = 0; i < nparts; ++i) { a += area2_partial[i]; ap += ap_partial[i]; }
@@ -481,15 +505,18 @@ int sort_scores(const float* scores, long long n, int* order, uint32_t* keys_sor
   return IEFVAD_OK;
 }
 
-int auc_ap(const float* scores, const int* pos, long long n, int repeat, double* out, int* order_out, cudaStream_t st) {
+int auc_ap_multi(const float* scores, const int* pos, const uint32_t* member, long long n, int repeat, int nsub,
+                 double* out, int* order_out, cudaStream_t st) {
   IEF_CHECK(n >= 0 && n < (1LL << 31), "auc_ap: bad n");
   IEF_CHECK(out && (n == 0 || (scores && pos)), "auc_ap: null argument");
   IEF_CHECK(repeat >= 1, "auc_ap: repeat must be >= 1");
+  IEF_CHECK(nsub >= 1 && nsub <= 32 && (member != nullptr || nsub == 1), "auc_ap: 1..32 subsets, a member mask when > 1");
   Tmp tmp(st);
   if (n == 0) {
     const double nan = __builtin_nan("");
-    const double h[4] = {nan, nan, 0.0, 0.0};
-    IEF_CUDA(cudaMemcpyAsync(out, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    double h[4 * 32];
+    for (int s = 0; s < nsub; ++s) { h[4 * s] = nan; h[4 * s + 1] = nan; h[4 * s + 2] = 0.0; h[4 * s + 3] = 0.0; }
+    IEF_CUDA(cudaMemcpyAsync(out, h, sizeof(double) * 4 * nsub, cudaMemcpyHostToDevice, st));
     IEF_CUDA(cudaStreamSynchronize(st));
     return IEFVAD_OK;
   }
@@ -506,25 +533,29 @@ int auc_ap(const float* scores, const int* pos, long long n, int repeat, double*
   IEF_TRY(tmp.get(&vb, n));
   IEF_TRY(tmp.get(&hist, size_t(RS_BINS) * nblocks));
   IEF_TRY(tmp.get(&totals, RS_BINS));
-  IEF_TRY(tmp.get(&tile_sums, ntiles));
-  IEF_TRY(tmp.get(&grand, 1));
-  IEF_TRY(tmp.get(&gtp, n));
-  IEF_TRY(tmp.get(&gfp, n));
+  IEF_TRY(tmp.get(&tile_sums, size_t(ntiles) * nsub));
+  IEF_TRY(tmp.get(&grand, nsub));
+  IEF_TRY(tmp.get(&gtp, size_t(n) * nsub));
+  IEF_TRY(tmp.get(&gfp, size_t(n) * nsub));
   const int term_blocks = ntiles < 256 ? ntiles : 256;
-  IEF_TRY(tmp.get(&area_part, term_blocks));
-  IEF_TRY(tmp.get(&ap_part, term_blocks));
+  IEF_TRY(tmp.get(&area_part, size_t(term_blocks) * nsub));
+  IEF_TRY(tmp.get(&ap_part, size_t(term_blocks) * nsub));
   rs_init_kernel<<<(nblocks < 1184 ? nblocks : 1184), RS_THREADS, 0, st>>>(scores, n, ka, va);
   count_launches(1);
   IEF_TRY(radix_sort_pairs(ka, va, kb, vb, n, hist, totals, st));
-  sc_reduce_kernel<<<ntiles, SC_THREADS, 0, st>>>(ka, va, pos, repeat, n, tile_sums);
-  sc_scan_tiles_kernel<<<1, SC_THREADS, 0, st>>>(tile_sums, ntiles, grand);
-  sc_apply_kernel<<<ntiles, SC_THREADS, 0, st>>>(ka, va, pos, repeat, n, tile_sums, gtp, gfp);
-  auc_terms_kernel<<<term_blocks, SC_THREADS, 0, st>>>(gtp, gfp, grand, area_part, ap_part);
-  auc_final_kernel<<<1, 1, 0, st>>>(area_part, ap_part, term_blocks, grand, out);
+  sc_reduce_kernel<<<dim3(ntiles, nsub), SC_THREADS, 0, st>>>(ka, va, pos, member, repeat, n, tile_sums);
+  sc_scan_tiles_kernel<<<nsub, SC_THREADS, 0, st>>>(tile_sums, ntiles, grand);
+  sc_apply_kernel<<<dim3(ntiles, nsub), SC_THREADS, 0, st>>>(ka, va, pos, member, repeat, n, tile_sums, gtp, gfp);
+  auc_terms_kernel<<<dim3(term_blocks, nsub), SC_THREADS, 0, st>>>(gtp, gfp, n, grand, area_part, ap_part);
+  auc_final_kernel<<<nsub, 1, 0, st>>>(area_part, ap_part, term_blocks, grand, out);
   count_launches(5);
   if (order_out) IEF_CUDA(cudaMemcpyAsync(order_out, va, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
+}
+
+int auc_ap(const float* scores, const int* pos, long long n, int repeat, double* out, int* order_out, cudaStream_t st) {
+  return auc_ap_multi(scores, pos, nullptr, n, repeat, 1, out, order_out, st);
 }
 
 }  // namespace iefvad

@@ -20,6 +20,11 @@ int sort_scores(const float* scores, long long n, int* order, uint32_t* keys_sor
 int auc_ap(const float* scores, const int* pos, long long n, int repeat, double* out, int* order_out,
            cudaStream_t stream);
 
+// The same for `nsub` <= 32 subsets of the segments at once (class-wise AUC / AP and Ano-AUC, train/ucf_test.py:164-178,
+// 336-353): bit s of member[j] = segment j belongs to subset s; out: device double[nsub][4].  One sort for all.
+int auc_ap_multi(const float* scores, const int* pos, const uint32_t* member, long long n, int repeat, int nsub,
+                 double* out, int* order_out, cudaStream_t stream);
+
 // dst[dst_off[s] + i] = src[src_off[s] + i] for i < len[s]; all index arrays on the device
 int segment_copy(const float* src, const long long* src_off, float* dst, const long long* dst_off,
                  const long long* len, long long nseg, cudaStream_t stream);

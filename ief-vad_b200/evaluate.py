@@ -108,18 +108,17 @@ class Evaluator:
         self._g_src, self._g_dst, self._g_len = i64(g_src), i64(g_dst), i64(g_len)
         # labels: positives per embedding row (gt is 16 raw frames per row, list/ucf_generate_gt.py:24)
         self.pos = torch.as_tensor(gt.reshape(-1, repeat).sum(axis=1).astype(np.int32), device=dev)
-        # class-wise / Ano-AUC subsets (train/ucf_test.py:164-178, 336-353), as segment-copy index lists
-        self.subsets: Dict[str, tuple] = {}
-        keys = list(dict.fromkeys(self.classes))
-        groups = {k: [v for v in range(n) if self.classes[v] == k] for k in keys}
-        groups["__abnormal__"] = [v for v in range(n) if self.classes[v] not in NORMAL_KEYS]
-        for k, vids in groups.items():
-            if not vids:
-                continue
-            ln = self.lengths[vids]
-            dst = np.concatenate([[0], np.cumsum(ln)])[:-1]
-            pos_sub = torch.cat([self.pos[int(self.global_off[v]):int(self.global_off[v] + self.lengths[v])] for v in vids])
-            self.subsets[k] = (i64(self.global_off[vids]), i64(dst), i64(ln), int(ln.sum()), pos_sub.contiguous())
+        # class-wise / Ano-AUC subsets (train/ucf_test.py:164-178, 336-353) as one membership bit mask per row:
+        # bit 0 = every row, bit 1 = rows of abnormal videos, bit 2 + c = rows of the c-th class key (list order)
+        self.class_keys = list(dict.fromkeys(self.classes))
+        if len(self.class_keys) > 30:
+            raise ValueError("at most 30 class keys (32 subsets per ranking pass)")
+        mask = np.zeros(self.total_rows, dtype=np.int64)
+        for v in range(n):
+            bits = 1 | (0 if self.classes[v] in NORMAL_KEYS else 2) | (4 << self.class_keys.index(self.classes[v]))
+            mask[int(self.global_off[v]):int(self.global_off[v] + self.lengths[v])] = bits
+        self.member = torch.as_tensor(mask.astype(np.uint32).view(np.int32), device=dev)
+        self.num_subsets = 2 + len(self.class_keys)
         self._img = self._ev = None
         self._pinned = None
 
@@ -166,31 +165,44 @@ class Evaluator:
             _segment_copy(allv, self._g_src, scores, self._g_dst, self._g_len)
         return scores
 
-    def metrics(self, scores: torch.Tensor) -> Dict[str, object]:
-        """AUC / AP overall, Ano-AUC and class-wise AUC / AP; one device->host read at the end."""
-        outs = [ops.auc_ap(scores, self.pos, self.repeat)]
-        names = ["__all__"]
-        for k, (src, dst, ln, total, pos_sub) in self.subsets.items():
-            sub = torch.empty(total, dtype=torch.float32, device=self.device)
-            _segment_copy(scores, src, sub, dst, ln)
-            outs.append(ops.auc_ap(sub, pos_sub, self.repeat))
-            names.append(k)
-        table = torch.stack(outs).cpu().numpy()
-        res: Dict[str, object] = {"AUC": float(table[0, 0]), "AP": float(table[0, 1]), "ano_AUC": float("nan"),
+    def metrics_async(self, scores: torch.Tensor) -> torch.Tensor:
+        """AUC / AP overall, Ano-AUC and class-wise AUC / AP from one ranking pass; the [num_subsets, 4] table is
+        copied to pinned host memory on the stream - nothing here waits for the device."""
+        table = ops.auc_ap_multi(scores, self.pos, self.member, self.num_subsets, self.repeat)
+        host = torch.empty(table.shape, dtype=table.dtype, pin_memory=True)
+        host.copy_(table, non_blocking=True)
+        return host
+
+    def finish(self, host_table: torch.Tensor) -> Dict[str, object]:
+        """Wait for the stream and unpack a metrics table returned by `metrics_async`."""
+        torch.cuda.current_stream(self.device).synchronize()
+        table = host_table.numpy()
+        res: Dict[str, object] = {"AUC": float(table[0, 0]), "AP": float(table[0, 1]),
+                                  "ano_AUC": float(table[1, 0]),      # NaN when one label value only (:347-350)
                                   "classwise": {}}
-        for name, row in zip(names[1:], table[1:]):
-            if name == "__abnormal__":
-                res["ano_AUC"] = float(row[0])          # NaN when only one label value is present (:347-350)
-            elif row[2] > 0:                            # classes without positives are skipped (:167-168)
+        for c, name in enumerate(self.class_keys):
+            row = table[2 + c]
+            if row[2] > 0:                              # classes without positives are skipped (:167-168)
                 res["classwise"][name] = (float(row[0]), float(row[1]))
         return res
 
-    def step(self, host_inputs: bool = False, with_metrics: bool = True) -> Dict[str, object]:
+    def metrics(self, scores: torch.Tensor) -> Dict[str, object]:
+        return self.finish(self.metrics_async(scores))
+
+    def step(self, host_inputs: bool = False, with_metrics: bool = True, sync: bool = True) -> Dict[str, object]:
+        """One evaluation pass.  With sync=False nothing waits for the device: the returned dict holds the device
+        score vector and, under "pending", the pinned metrics table to hand to `finish()` later."""
         if host_inputs:
             self._img.copy_(self._pinned[0], non_blocking=True)
             self._ev.copy_(self._pinned[1], non_blocking=True)
         scores = self.gather(self.local_scores())
-        res = self.metrics(scores) if with_metrics else {}
+        res: Dict[str, object] = {}
+        if with_metrics:
+            pending = self.metrics_async(scores)
+            if sync:
+                res = self.finish(pending)
+            else:
+                res["pending"] = pending
         res["scores"] = scores
         return res
 
@@ -200,4 +212,4 @@ class Evaluator:
                                                                              if self._pinned else 2)
 
     def d2h_bytes(self) -> int:
-        return (1 + len(self.subsets)) * 4 * 8
+        return self.num_subsets * 4 * 8

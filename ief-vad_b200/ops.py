@@ -157,3 +157,21 @@ def auc_ap(scores, pos, repeat: int = 16, return_order: bool = False):
         _lib.check(_lib.lib.iefvad_auc_ap(s.data_ptr(), p.data_ptr(), s.numel(), repeat, out.data_ptr(),
                                           _lib.ptr(order), _stream(s)))
     return (out, order) if return_order else out
+
+
+def auc_ap_multi(scores, pos, member, num_subsets: int, repeat: int = 16):
+    """AUC / AP of `num_subsets` (<= 32) subsets of the segments from ONE ranking pass (class-wise AUC / AP and
+    Ano-AUC, train/ucf_test.py:164-178, 336-353).  member[j] bit s = segment j is in subset s.
+    -> float64 tensor [num_subsets, 4] on the device (AUC, AP, #positive frames, #negative frames)."""
+    s = _f32c(scores, "auc_ap_multi").reshape(-1)
+    p = pos.to(device=s.device, dtype=torch.int32).contiguous().reshape(-1)
+    m = member.to(device=s.device).contiguous().reshape(-1)
+    if m.dtype not in (torch.int32, torch.uint32):
+        raise RuntimeError("auc_ap_multi: member must be a 32-bit mask tensor")
+    if p.numel() != s.numel() or m.numel() != s.numel():
+        raise RuntimeError(f"auc_ap_multi: {s.numel()} scores, {p.numel()} label counts, {m.numel()} masks")
+    out = torch.empty((num_subsets, 4), dtype=torch.float64, device=s.device)
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib.iefvad_auc_ap_multi(s.data_ptr(), p.data_ptr(), m.data_ptr(), s.numel(), repeat,
+                                                num_subsets, out.data_ptr(), None, _stream(s)))
+    return out

@@ -98,7 +98,8 @@ int iefvad_layernorm(const float* x, int64_t rows, int dim, const float* w1, con
 
 /* nn.Linear with fused epilogue: out = (resid ? resid : 0) + alpha * act(x W^T + bias); act: 0 none, 1 ReLU,
  * 2 QuickGELU (model/module.py:15-17).  x [rows, in_f] fp32, w [out_f, in_f] fp32, out [rows, out_f] fp32.
- * plan: -1 fp32 FFMA, 0 bf16 tcgen05, 1 split-bf16 tcgen05.  tile_n: 0 = heuristic, or 64 / 128 / 256. */
+ * plan: -1 fp32 FFMA, 0 bf16 tcgen05, 1 split-bf16 tcgen05.  tile_n: 0 = heuristic, or 64 / 128 / 256 (one CTA per
+ * 128-row tile), or 512 = 256-column tiles on CTA pairs (tcgen05 cta_group::2, 256-row tiles; out_f %% 256 == 0). */
 int iefvad_linear(const float* x, const float* w, const float* bias, const float* resid, float alpha, int act,
                   int64_t rows, int in_f, int out_f, int plan, int tile_n, float* out, void* stream);
 
@@ -140,6 +141,14 @@ int iefvad_sort_scores(const float* scores, int64_t n, int32_t* order, void* str
 int iefvad_auc_ap(const float* scores, const int32_t* pos, int64_t n, int repeat, double* out, int32_t* order,
                   void* stream);
 
+/* The same for `num_subsets` (1..32) subsets of the segments in ONE ranking pass - the class-wise AUC / AP loop of
+ * train/ucf_test.py:164-178 and compute_ano_auc (:336-353), which re-run sklearn per class on concatenated slices.
+ * member [n] uint32: bit s set = segment belongs to subset s (NULL allowed when num_subsets == 1).  A subset's
+ * AUC / AP equals ranking its members alone: the stable sort keeps their relative order and tie groups without
+ * members contribute nothing.  out: DEVICE double[num_subsets][4] laid out as for iefvad_auc_ap. */
+int iefvad_auc_ap_multi(const float* scores, const int32_t* pos, const uint32_t* member, int64_t n, int repeat,
+                        int num_subsets, double* out, int32_t* order, void* stream);
+
 /* Segmented copy: dst[dst_off[s] + i] = src[src_off[s] + i] for i < len[s] (all arrays on the device, int64).
  * Drops the zero-pad rows of chunked videos (train/ucf_test.py:113 `logits1[0:len_cur]`), and re-orders the
  * per-rank score vectors into list order after the multi-GPU gather. */
@@ -151,7 +160,7 @@ int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, co
  * ---------------------------------------------------------------------------------------------- */
 
 /* Micro-benchmark of the tcgen05 GEMM on library-allocated buffers (synchronises; default stream): M x N x K,
- * nsplit 1 | 3, tile_n 0 | 64 | 128 | 256, stages 0 (= as many as fit) or a cap on the operand ring depth, epi_kind 0 = mainloop only (discard), 1 = fp32 out, 2 = refinement
+ * nsplit 1 | 3, tile_n 0 | 64 | 128 | 256 | 512 (as for iefvad_linear), stages 0 (= as many as fit) or a cap on the operand ring depth, epi_kind 0 = mainloop only (discard), 1 = fp32 out, 2 = refinement
  * epilogue (fp32 residual in, fp32 + bf16 hi/lo out), 3 = ReLU -> bf16 hi/lo, 4 = QKV scatter.  Writes the mean
  * device time of `iters` back-to-back launches (CUDA events). */
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,

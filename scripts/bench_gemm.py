@@ -11,7 +11,7 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 EPI = {0: "discard", 1: "f32", 2: "refine(resid,f32,hi,lo)", 3: "relu->hi,lo", 4: "qkv"}
 print(f"{'N':>5} {'K':>5} {'split':>5} {'BN':>4} {'stg':>3} {'epilogue':>24} {'ms':>8} {'TF/s alg':>9} {'TF/s mma':>9}")
 cases = []
-for bn in (256, 128):
+for bn in (512, 256):
     for nsplit in (1, 3):
         for st in (0, 3):
             cases.append((768, 768, nsplit, bn, st, 0))

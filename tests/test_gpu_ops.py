@@ -64,7 +64,8 @@ def test_layernorm_single_and_double(ops, D):
 @pytest.mark.parametrize("plan", ["fp32", "split", "bf16"])
 @pytest.mark.parametrize("rows,in_f,out_f,tile_n", [
     (256, 768, 768, 0), (1000, 768, 2304, 0), (130, 768, 1536, 64), (4096, 768, 768, 128),
-    (4096, 768, 768, 256), (1, 768, 768, 0), (257, 128, 96, 0), (300, 3072, 768, 0), (20000, 768, 768, 0)])
+    (4096, 768, 768, 256), (1, 768, 768, 0), (257, 128, 96, 0), (300, 3072, 768, 0), (20000, 768, 768, 0),
+    (4096, 768, 768, 512), (1000, 768, 2304, 512), (130, 768, 1536, 512), (20000, 768, 768, 512), (257, 128, 256, 512)])
 def test_linear_plain(ops, plan, rows, in_f, out_f, tile_n):
     if plan == "fp32" and tile_n:
         pytest.skip("tile_n only applies to the tcgen05 plans")
@@ -80,14 +81,18 @@ def test_linear_plain(ops, plan, rows, in_f, out_f, tile_n):
 
 @pytest.mark.parametrize("plan", ["fp32", "split", "bf16"])
 @pytest.mark.parametrize("act", ["relu", "quickgelu", None])
-def test_linear_epilogue_residual_alpha_act(ops, plan, act):
+@pytest.mark.parametrize("rows,tile_n", [(333, 0), (333, 512), (5000, 512), (5000, 256)])
+def test_linear_epilogue_residual_alpha_act(ops, plan, act, rows, tile_n):
+    if plan == "fp32" and tile_n:
+        pytest.skip("tile_n only applies to the tcgen05 plans")
     rng = np.random.default_rng(5)
-    rows, D = 333, 768
+    D = 768
     x = rng.standard_normal((rows, D)).astype(np.float32)
     w = (rng.standard_normal((D, D)) / np.sqrt(D)).astype(np.float32)
     b = rng.standard_normal(D).astype(np.float32)
     r = rng.standard_normal((rows, D)).astype(np.float32)
-    got = ops.linear(_cuda(x), _cuda(w), _cuda(b), resid=_cuda(r), alpha=-0.5, act=act, plan=plan).cpu().numpy()
+    got = ops.linear(_cuda(x), _cuda(w), _cuda(b), resid=_cuda(r), alpha=-0.5, act=act, plan=plan,
+                     tile_n=tile_n).cpu().numpy()
     y = O.linear(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64))
     if act == "relu":
         y = np.maximum(y, 0)

@@ -98,6 +98,41 @@ def test_auc_ap_matches_live_sklearn_and_oracle(ops, n, ties):
         assert abs(got[1] - sk.average_precision_score(_frames(pos), rep)) < 1e-12
 
 
+@pytest.mark.parametrize("n,nsub,ties", [(3000, 5, True), (77788, 16, False), (40000, 32, True)])
+def test_auc_ap_multi_equals_per_subset_ranking(ops, n, nsub, ties):
+    """Class-wise AUC / AP from ONE ranking pass == ranking every subset on its own (oracle / sklearn semantics),
+    including subsets with one label value only (NaN AUC), empty subsets and ties across subset boundaries."""
+    rng = np.random.default_rng(n + nsub)
+    s = rng.random(n).astype(np.float32)
+    if ties:
+        s = np.round(s, 2)
+    pos = np.where(rng.random(n) < 0.2, rng.integers(1, 17, n), 0).astype(np.int32)
+    cls = rng.integers(0, nsub - 2, n) if nsub > 2 else np.zeros(n, dtype=np.int64)
+    member = np.ones(n, dtype=np.uint32)                      # bit 0: everything
+    member |= np.where(cls % 2 == 1, 2, 0).astype(np.uint32)  # bit 1: an "abnormal"-style union of classes
+    for c in range(nsub - 2):
+        member |= np.where(cls == c, np.uint32(4) << np.uint32(c), 0).astype(np.uint32)
+    if nsub > 3:
+        pos[cls == 0] = 0                                     # a class without positives -> AUC NaN, AP 0
+    if nsub == 32:
+        member &= ~np.uint32(1 << 31)                         # the last subset is empty
+    got = ops.auc_ap_multi(torch.from_numpy(s).cuda(), torch.from_numpy(pos).cuda(),
+                           torch.from_numpy(member.view(np.int32)).cuda(), nsub).cpu().numpy()
+    for k in range(nsub):
+        sel = ((member >> np.uint32(k)) & 1).astype(bool)
+        if not sel.any():
+            assert np.isnan(got[k, 0]) and got[k, 2] == 0 and got[k, 3] == 0
+            continue
+        auc, ap = O.auc_ap_segments(s[sel], pos[sel], 16)
+        assert got[k, 2] == pos[sel].sum() and got[k, 3] == 16 * sel.sum() - pos[sel].sum()
+        if np.isnan(auc):
+            assert np.isnan(got[k, 0])
+        else:
+            assert abs(got[k, 0] - auc) < 1e-12, (k, got[k, 0], auc)
+        if pos[sel].sum() > 0:
+            assert abs(got[k, 1] - ap) < 1e-12, (k, got[k, 1], ap)
+
+
 def test_auc_stress_2_pow_24(ops):
     """SURVEY 8d stress point: N = 2^24 scores, 5 % positives, 10 % forced ties; checked through size-independent
     properties (sortedness of the rank permutation, permutation validity, invariance to input order)."""
