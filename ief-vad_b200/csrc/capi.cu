@@ -3,10 +3,12 @@
 
 #include <cmath>
 #include <new>
+#include <vector>
 
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "graph.cuh"
 #include "model.cuh"
 #include "rank.cuh"
 
@@ -290,6 +292,48 @@ int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, co
   return segment_copy(src, reinterpret_cast<const long long*>(src_off), dst,
                       reinterpret_cast<const long long*>(dst_off), reinterpret_cast<const long long*>(len), nseg,
                       static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ rows D1-D4
+
+int iefvad_distance_adj(int64_t batch_size, int max_seqlen, float* out, void* stream) {
+  return distance_adj(out, batch_size, max_seqlen, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_similarity_adj(const float* x, const float* weight0_t, const int64_t* seq_len_host, int64_t B, int T, int in_f,
+                          int out_f, int plan, float* out, void* stream) {
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return similarity_adj(x, weight0_t, reinterpret_cast<const long long*>(seq_len_host), B, T, in_f, out_f, plan, out, sms,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_graph_convolution(const float* x, const float* adj, const float* weight_t, const float* bias, int residual,
+                             const float* conv_w, const float* conv_b, int64_t B, int T, int in_f, int out_f, int plan,
+                             float* out, void* stream) {
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return graph_convolution(x, adj, weight_t, bias, residual, conv_w, conv_b, B, T, in_f, out_f, plan, out, sms,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_distance_scan(const float* s, int64_t B, int T, int D, float* y, void* stream) {
+  return distance_scan(s, B, T, D, y, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_transformer(const float* x, const float* const* params, int layers, int L, int N, int D, int heads,
+                       const float* attn_mask, const uint8_t* key_padding_mask, int plan, float* out, void* stream) {
+  IEF_CHECK(params != nullptr || layers == 0, "iefvad_transformer: null parameter table");
+  IEF_CHECK(layers >= 0 && layers <= 64, "iefvad_transformer: 0..64 layers");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  std::vector<ResBlockParams> blocks(static_cast<size_t>(layers));
+  for (int i = 0; i < layers; ++i) {
+    const float* const* p = params + 12 * i;
+    blocks[i] = ResBlockParams{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11]};
+  }
+  return transformer(x, blocks.data(), layers, L, N, D, heads, attn_mask, key_padding_mask, plan, out, sms,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,

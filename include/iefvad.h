@@ -156,6 +156,40 @@ int iefvad_segment_copy(const float* src, const int64_t* src_off, float* dst, co
                         const int64_t* len, int64_t nseg, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The VadCLIP-style graph / transformer classes named by the north star (model/layers.py, model/module.py; not
+ * wired into the live reference graph).  plan: -1 fp32 FFMA (feature sizes %% 16), 0 bf16 / 1 split-bf16 tcgen05
+ * (feature sizes %% 64).  Weights are passed TRANSPOSED ([out_f, in_f] contiguous; the reference stores [in_f, out_f]).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* DistanceAdj.forward(batch_size, max_seqlen), model/layers.py:172-179: out[b, i, j] = exp(-|i-j| / e). */
+int iefvad_distance_adj(int64_t batch_size, int max_seqlen, float* out, void* stream);
+
+/* SimilarityAdj.forward(input, seq_len), model/layers.py:130-158.  x [B, T, in_f]; weight0_t = weight0^T
+ * [out_f, in_f]; seq_len_host: HOST int64[B] or NULL; out [B, T, T] (cosine of theta = x W0 with itself,
+ * threshold 0.7, row softmax on the top-left len x len block, zeros elsewhere). */
+int iefvad_similarity_adj(const float* x, const float* weight0_t, const int64_t* seq_len_host, int64_t B, int T, int in_f,
+                          int out_f, int plan, float* out, void* stream);
+
+/* GraphConvolution.forward(input, adj), model/layers.py:91-106: out = adj @ (x @ W) (+ bias) + residual.
+ * residual: 0 none, 1 identity (in_f == out_f), 2 Conv1d(in_f -> out_f, k = 5, pad = 2) with conv_w [out_f, 5, in_f]
+ * (= the reference's [out_f, in_f, 5] with the last two axes swapped) and conv_b [out_f].
+ * adj [B, T, T], or NULL = the DistanceAdj adjacency evaluated as a bidirectional first-order scan over T. */
+int iefvad_graph_convolution(const float* x, const float* adj, const float* weight_t, const float* bias, int residual,
+                             const float* conv_w, const float* conv_b, int64_t B, int T, int in_f, int out_f, int plan,
+                             float* out, void* stream);
+
+/* y[b, t, :] = sum_k exp(-|t-k| / e) s[b, k, :]  ==  DistanceAdj(B, T) @ s, as forward + backward linear
+ * recurrences (segment reduce, carry scan, apply).  s, y [B, T, D] fp32. */
+int iefvad_distance_scan(const float* s, int64_t B, int T, int D, float* y, void* stream);
+
+/* Transformer.forward((x, padding_mask)), model/module.py:20-54, x SEQ-FIRST [L, N, D]; params: HOST array of
+ * layers * 12 device pointers per block in the order ln_1.weight, ln_1.bias, attn.in_proj_weight, attn.in_proj_bias,
+ * attn.out_proj.weight, attn.out_proj.bias, ln_2.weight, ln_2.bias, mlp.c_fc.weight, mlp.c_fc.bias,
+ * mlp.c_proj.weight, mlp.c_proj.bias.  attn_mask: optional additive [L, L]; key_padding_mask: optional [N, L] uint8. */
+int iefvad_transformer(const float* x, const float* const* params, int layers, int L, int N, int D, int heads,
+                       const float* attn_mask, const uint8_t* key_padding_mask, int plan, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Instrumentation used by bench.py
  * ---------------------------------------------------------------------------------------------- */
 

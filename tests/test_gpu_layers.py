@@ -1,0 +1,134 @@
+"""Rows D1-D4 (model/layers.py, model/module.py): CUDA path vs the reference's golden outputs and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import iefvad_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 2e-5, "split": 5e-5, "bf16": 3e-2}
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from iefvad_b200 import layers, module
+    return layers, module
+
+
+@pytest.fixture(scope="module")
+def z():
+    return load_golden("layers.npz")
+
+
+def _c(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 50), (1, 256), (3, 1000)])
+def test_distance_adj(mods, B, T):
+    layers, _ = mods
+    got = layers.DistanceAdj().cuda()(B, T).cpu().numpy()
+    ref = O.distance_adj(B, T)
+    assert got.shape == ref.shape
+    # fp32 exp(x) carries a relative error of ~|x| ulp (|x| reaches 87 before the result goes denormal); denormal
+    # results are compared absolutely
+    np.testing.assert_allclose(got, ref, rtol=3e-5, atol=1e-37)
+
+
+@pytest.mark.parametrize("B,T,D", [(2, 50, 128), (1, 1, 64), (3, 257, 96), (1, 4096, 768), (2, 64, 768), (1, 129, 130)])
+def test_distance_scan_equals_dense_adjacency_product(mods, B, T, D):
+    layers, _ = mods
+    rng = np.random.default_rng(T)
+    s = rng.standard_normal((B, T, D)).astype(np.float32)
+    got = layers.distance_scan(_c(s)).cpu().numpy()
+    if T <= 1024:
+        ref = O.distance_adj(B, T, np.float64) @ s.astype(np.float64)
+    else:
+        ref = O.graph_convolution_distance_scan(s.astype(np.float64), np.eye(D))
+    assert O.max_norm_err(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize("plan", ["fp32", "split", "bf16"])
+def test_similarity_adj_vs_reference_golden(mods, z, plan):
+    layers, _ = mods
+    x, w0 = z["sim:x"], z["sim:w0"]
+    m = layers.SimilarityAdj(w0.shape[0], w0.shape[1]).cuda()
+    m.weight0.data.copy_(_c(w0))
+    m.precision = plan
+    for key, seq in (("sim:out_none", None), ("sim:out_len", [int(v) for v in z["sim:seq_len"]])):
+        got = m(_c(x), seq).cpu().numpy()
+        ref = z[key]
+        # the 0.7 threshold is discontinuous: an entry whose cosine sits within the plan's rounding error of 0.7 may
+        # legitimately flip, which moves its whole row; compare the rows without such an entry
+        theta = x.astype(np.float64) @ w0.astype(np.float64)
+        nrm = np.sqrt((theta * theta).sum(-1, keepdims=True))
+        cos = theta @ theta.transpose(0, 2, 1) / (nrm @ nrm.transpose(0, 2, 1) + 1e-20)
+        margin = {"fp32": 1e-5, "split": 1e-4, "bf16": 3e-2}[plan]
+        safe = ~(np.abs(cos - 0.7) < margin).any(axis=2)
+        assert safe.mean() > (0.9 if plan != "bf16" else 0.0)
+        if safe.any():
+            assert np.abs(got[safe] - ref[safe]).max() / np.abs(ref).max() < TOL[plan]
+        assert np.array_equal(got == 0, ref == 0) or plan == "bf16" or not safe.all()
+
+
+@pytest.mark.parametrize("plan", ["fp32", "split", "bf16"])
+def test_graph_convolution_vs_reference_golden(mods, z, plan):
+    layers, _ = mods
+    x, adj = z["sim:x"], z["gc:adj"]
+    gc = layers.GraphConvolution(128, 128, bias=True, residual=True).cuda()
+    gc.weight.data.copy_(_c(z["gc:w"]))
+    gc.bias.data.copy_(_c(z["gc:b"]))
+    gc.precision = plan
+    got = gc(_c(x), _c(adj)).cpu().numpy()
+    assert O.max_norm_err(got, z["gc:out"]) < TOL[plan]
+    gc2 = layers.GraphConvolution(128, 256, bias=False, residual=True).cuda()     # Conv1d residual (Din != Dout)
+    gc2.weight.data.copy_(_c(z["gc2:w"]))
+    gc2.residual.weight.data.copy_(_c(z["gc2:conv_w"]))
+    gc2.residual.bias.data.copy_(_c(z["gc2:conv_b"]))
+    gc2.precision = plan
+    got2 = gc2(_c(x), _c(adj)).cpu().numpy()
+    assert O.max_norm_err(got2, z["gc2:out"]) < TOL[plan]
+    gc3 = layers.GraphConvolution(128, 128, bias=False, residual=False).cuda()
+    gc3.weight.data.copy_(_c(z["gc:w"]))
+    gc3.precision = plan
+    got3 = gc3(_c(x), _c(adj)).cpu().numpy()
+    ref3 = O.graph_convolution(x.astype(np.float64), adj.astype(np.float64), z["gc:w"].astype(np.float64), None, "none")
+    assert O.max_norm_err(got3, ref3) < TOL[plan]
+
+
+@pytest.mark.parametrize("plan", ["fp32", "split"])
+@pytest.mark.parametrize("B,T,D", [(2, 50, 128), (1, 1000, 256), (1, 256, 768)])
+def test_graph_convolution_distance_scan_equals_dense(mods, plan, B, T, D):
+    """adj=None (scan form of the DistanceAdj adjacency) == the dense product with DistanceAdj's matrix."""
+    layers, _ = mods
+    torch.manual_seed(T)
+    gc = layers.GraphConvolution(D, D, bias=True, residual=True).cuda()
+    gc.precision = plan
+    x = torch.randn(B, T, D, device="cuda")
+    adj = layers.DistanceAdj().cuda()(B, T)
+    dense = gc(x, adj).cpu().numpy()
+    scan = gc(x, None).cpu().numpy()
+    ref = O.graph_convolution(x.cpu().numpy().astype(np.float64), O.distance_adj(B, T, np.float64),
+                              gc.weight.detach().cpu().numpy().astype(np.float64),
+                              gc.bias.detach().cpu().numpy().astype(np.float64), "identity")
+    assert O.max_norm_err(scan, ref) < TOL[plan]
+    assert O.max_norm_err(dense, ref) < TOL[plan]
+
+
+@pytest.mark.parametrize("plan", ["fp32", "split", "bf16"])
+def test_transformer_vs_reference_golden(mods, z, plan):
+    _, module = mods
+    W, heads = z["tr:x"].shape[-1], int(z["tr:heads"])
+    layers_n = len({k.split(".")[1] for k in z.files if k.startswith("tr:param:resblocks.")})
+    tr = module.Transformer(W, layers_n, heads, attn_mask=_c(z["tr:mask"])).cuda().eval()
+    tr.load_state_dict({k[len("tr:param:"):]: _c(z[k]) for k in z.files if k.startswith("tr:param:")})
+    tr.precision = plan
+    x = _c(z["tr:x"])
+    pad = _c(z["tr:pad"])
+    tol = {"fp32": 3e-5, "split": 2e-3, "bf16": 3e-2}[plan]     # "split": attention P.V itself stays single-pass bf16
+    out_m, pad_back = tr((x, pad))
+    assert pad_back is pad
+    assert O.max_norm_err(out_m.cpu().numpy(), z["tr:out_masked"]) < tol
+    out_p, _ = tr((x, None))
+    assert O.max_norm_err(out_p.cpu().numpy(), z["tr:out_nopad"]) < tol
