@@ -33,6 +33,12 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 FLOPS_PER_FRAME_T256 = 47_187_456 + 12_288 * 256          # SURVEY.md 8d, algorithmic
+# operand types of the tensor-core contractions per precision plan (accumulation, residual stream, LayerNorm, softmax
+# statistics, fusion and classifier are fp32 in every plan)
+DTYPES = {"H": "bf16 (encoder, heads: 3-term split) + fp16 (refinement) operands, fp32 accumulate",
+          "B": "bf16 operands (heads + refinement: 3-term split), fp32 accumulate",
+          "A": "bf16 operands (heads: 3-term split), fp32 accumulate", "bf16": "bf16 operands, fp32 accumulate",
+          "split": "bf16 operands, 3-term split everywhere, fp32 accumulate", "fp32": "f32"}
 
 
 def peaks():
@@ -200,7 +206,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ucf", choices=["ucf", "xd", "c1"])
-    ap.add_argument("--plan", default=None, help="precision plan override: B (default), A, bf16, split, fp32")
+    ap.add_argument("--plan", default=None, help="precision plan override: H (default), B, A, bf16, split, fp32")
     ap.add_argument("--cpu-sample", type=int, default=24, help="videos in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -288,13 +294,24 @@ def main():
         for _ in range(2):
             evaluator.step(host_inputs=True)
         ms_e2e, _ = timed(True, max(2, args.steps // 2))
+        # ---- the all-bf16-operand plan B beside the default (context: same accuracy, 3x the refinement MMAs)
+        alt = None
+        if str(model.temporal.precision) == "H" and not args.plan:
+            evaluator.set_device_features(img_c, ev_c)
+            model.temporal.precision = "B"
+            for _ in range(3):
+                evaluator.step()
+            ms_b, _ = timed(False, max(3, args.steps // 2))
+            alt = {"B": {"ms_per_step": round(ms_b, 4), "value": round(frames_total / (ms_b * 1e-3), 1),
+                         "dtype": DTYPES["B"]}}
+            model.temporal.precision = "H"
         # ---- per-kernel-class profile of one step (CUDA events around every launch of the forward)
         evaluator.set_device_features(img_c, ev_c)
         import ctypes as C
         _lib.lib.iefvad_profile_enable(1)
         evaluator.step(with_metrics=False)
         torch.cuda.synchronize()
-        ms_k, work_k, n_k = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_int64 * 8)()
+        ms_k, work_k, n_k = (C.c_double * 12)(), (C.c_double * 12)(), (C.c_int64 * 12)()
         _lib.check(_lib.lib.iefvad_profile_read(ms_k, work_k, n_k))
         _lib.lib.iefvad_profile_enable(0)
 
@@ -304,22 +321,43 @@ def main():
         return
 
     pk = peaks()
-    names = ["gemm_tc", "attn_tc", "layernorm", "fuse", "classifier", "ingest", "gemm_simt", "attn_simt"]
+    names = ["gemm_qkv", "attn_tc", "layernorm", "fuse", "classifier", "ingest", "gemm_simt", "attn_simt",
+             "gemm_out_proj", "gemm_heads", "gemm_refine1", "gemm_refine2"]
+    flop_classes = (0, 1, 6, 7, 8, 9, 10, 11)
     kernels = {}
     for i, nm in enumerate(names):
         if n_k[i]:
             rate = work_k[i] / (ms_k[i] * 1e-3)
             kernels[nm] = {"launches": int(n_k[i]), "ms": round(ms_k[i], 4),
-                           ("tflops" if i in (0, 1, 6, 7) else "gbs"): round(rate / (1e12 if i in (0, 1, 6, 7) else 1e9), 2)}
-    gemm_tflops = work_k[0] / (ms_k[0] * 1e-3) / 1e12 if n_k[0] else 0.0
+                           ("tflops" if i in flop_classes else "gbs"): round(rate / (1e12 if i in flop_classes else 1e9), 2)}
+    gemm_ids = (0, 8, 9, 10, 11)
+    gemm_ms = sum(ms_k[i] for i in gemm_ids)
+    gemm_tflops = sum(work_k[i] for i in gemm_ids) / (gemm_ms * 1e-3) / 1e12 if gemm_ms else 0.0
+    kernels["gemm_tc_all"] = {"launches": int(sum(n_k[i] for i in gemm_ids)), "ms": round(gemm_ms, 4),
+                              "tflops": round(gemm_tflops, 2)}
+    # roofline of the dominant kernel: the refinement Linears (80 of the 120 tcgen05 GEMM launches of a step, all
+    # M x 768 x 768): algorithmic FLOPs per launch / mean CUDA-event duration of those launches
+    ref_ms = ms_k[10] + ms_k[11]
+    ref_n = int(n_k[10] + n_k[11])
     peak_tf = float(pk["bf16_tflops_sustained"])
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16, fp32 accumulate)",
-                "achieved": round(gemm_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(gemm_tflops / peak_tf, 4), "traffic": None,
+    ref_tflops = (work_k[10] + work_k[11]) / (ref_ms * 1e-3) / 1e12 if ref_ms else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get("gemm_refine_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256, ROWMAJOR, *, CG2>: refinement Linears (tcgen05 bf16, fp32 accumulate)",
+                "achieved": round(ref_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(ref_tflops / peak_tf, 4), "traffic": traffic,
+                "launches": ref_n, "ms_per_launch": round(ref_ms / max(ref_n, 1), 5),
                 "peak_source": f"{pk['source']} sustained bf16 (MEASURED_PEAKS.json)",
-                "note": "algorithmic FLOPs (2MNK per launch; the 3-term bf16 split's extra MMAs are not counted) / "
-                        "sum of CUDA-event durations of the GEMM launches of one step",
-                "share_of_step": round(ms_k[0] / max(sum(ms_k), 1e-9), 4)}
+                "note": "algorithmic FLOPs (2*M*768*768 per launch; the 3-term bf16 split of plan B issues 3x the MMAs, "
+                        "not counted) / mean CUDA-event duration of the refinement GEMM launches of one step; traffic = "
+                        "dram bytes per launch from the ncu --set full capture in profiles/ (null until captured)",
+                "share_of_step": round(ref_ms / max(sum(ms_k), 1e-9), 4),
+                "all_gemms": {"achieved": round(gemm_tflops, 2), "frac": round(gemm_tflops / peak_tf, 4),
+                              "share_of_step": round(gemm_ms / max(sum(ms_k), 1e-9), 4)}}
 
     value = frames_total / (ms_dev * 1e-3)
     e2e_val = frames_total / (ms_e2e * 1e-3)
@@ -330,7 +368,8 @@ def main():
     line = {
         "metric": "fused frames/sec (IEF-VAD inference)", "value": round(value, 1), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_dev, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES.get(str(model.temporal.precision), "bf16"),
+        "data": "synthetic",
         "config": {"workload": workload_names[args.workload] + (f" x {world} ranks (one set per rank)" if world > 1 else ""),
                    "videos": int(len(wl["lengths"])), "valid_frames": frames_total,
                    "rows_incl_pad_per_rank": rows_local, "precision_plan": model.temporal.precision,
@@ -343,6 +382,7 @@ def main():
         "roofline": roofline,
         "kernels": kernels,
         "frame_auc": res["AUC"], "frame_ap": res["AP"],
+        "other_plans": alt,
         "forward_tflops_algorithmic": round(rows_local * world * FLOPS_PER_FRAME_T256 / (ms_dev * 1e-3) / 1e12, 2),
         "cpu_baseline": cpu,
     }

@@ -18,10 +18,12 @@ namespace iefvad {
 namespace {
 
 constexpr int QB = 128;   // query rows per CTA
-constexpr int KB = 128;   // keys per block
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int DH, int DHP>
+// KB = keys per block.  KB = 64 halves every per-CTA resource (104 KB smem, 256 TMEM columns) so that TWO CTAs share
+// an SM and one CTA's softmax overlaps the other's MMAs / loads - the short-sequence configuration (T_c = 256 has
+// only two 128-key blocks to pipeline within a CTA); KB = 128 halves the per-key synchronisation for long T.
+template <int DH, int DHP, int KB>
 struct AttnCfg {
   static constexpr uint32_t kQBytes = QB * DHP * 2;
   static constexpr uint32_t kKBytes = KB * DHP * 2;
@@ -33,16 +35,18 @@ struct AttnCfg {
   static constexpr uint32_t kOffP = kOffV + 2 * kVBytes;
   static constexpr uint32_t kOffBar = kOffP + kPBytes;
   static constexpr size_t kSmemBytes = 1024 + kOffBar + 256;
-  static constexpr uint32_t kTmemCols = 512;             // S0 [0,128) S1 [128,256) O [256,256+DH)
+  static constexpr uint32_t kOffO = 2 * KB;              // TMEM: S0 [0,KB) S1 [KB,2KB) O [2KB, 2KB+DH)
+  static constexpr uint32_t kTmemCols = (2 * KB + 128 <= 256) ? 256 : 512;
+  static constexpr int kCtasPerSm = (KB == 64) ? 2 : 1;
 };
 
-template <int DH, int DHP>
-__global__ void __launch_bounds__(192, 1)
+template <int DH, int DHP, int KB>
+__global__ void __launch_bounds__(192, AttnCfg<DH, DHP, KB>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H,
                const float* __restrict__ attn_mask /* [T,T] additive or null */,
                const uint8_t* __restrict__ key_pad /* [B,T] 1 = ignore, or null */) {
-  using Cfg = AttnCfg<DH, DHP>;
+  using Cfg = AttnCfg<DH, DHP, KB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
@@ -140,7 +144,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         const uint32_t sp = smem_u32(smem + Cfg::kOffP);
         const uint32_t sv = smem_u32(smem + Cfg::kOffV + s * Cfg::kVBytes);
-        const uint32_t d = tmem_base + 256u;
+        const uint32_t d = tmem_base + Cfg::kOffO;
 #pragma unroll
         for (int kk = 0; kk < KB / 16; ++kk) {
           const int c = kk >> 2, k4 = kk & 3;
@@ -203,7 +207,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c) {
           float v[32];
-          tmem_ld32(tmem_base + 256u + lane_off + uint32_t(c * 32), v);
+          tmem_ld32(tmem_base + Cfg::kOffO + lane_off + uint32_t(c * 32), v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += v[i];
@@ -265,7 +269,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
     for (int c = 0; c < DH / 32; ++c) {
       float v[32];
-      tmem_ld32(tmem_base + 256u + lane_off + uint32_t(c * 32), v);
+      tmem_ld32(tmem_base + Cfg::kOffO + lane_off + uint32_t(c * 32), v);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += v[i];
@@ -293,12 +297,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-template <int DH, int DHP>
+template <int DH, int DHP, int KB>
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
-  using Cfg = AttnCfg<DH, DHP>;
+  using Cfg = AttnCfg<DH, DHP, KB>;
   static bool attr_set = false;
   if (!attr_set) {
-    IEF_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DH, DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IEF_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DH, DHP, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(Cfg::kSmemBytes)));
     attr_set = true;
   }
@@ -308,7 +312,7 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
   IEF_TRY(make_tmap_3d(&tk, a.k, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, KB, 1));
   IEF_TRY(make_tmap_3d(&tv, a.vt, a.T, DH, BH, uint64_t(a.Tpad) * 2, uint64_t(DH) * a.Tpad * 2, 64, DH, 1));
   dim3 grid((a.T + QB - 1) / QB, a.H, a.B);
-  attn_tc_kernel<DH, DHP><<<grid, 192, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, a.attn_mask,
+  attn_tc_kernel<DH, DHP, KB><<<grid, 192, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, a.attn_mask,
                                                                   a.key_pad);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
@@ -399,10 +403,16 @@ int attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
   IEF_CHECK(a.Tpad % 8 == 0 && a.Tpad >= a.T, "attn_tc: Tpad=%d must be a multiple of 8 and >= T=%d", a.Tpad, a.T);
   IEF_CHECK(a.ldo % 8 == 0, "attn_tc: ldo must be a multiple of 8");
   IEF_CHECK(a.B <= 65535 && a.H <= 65535, "attn_tc: B=%d / H=%d exceed the grid limits", a.B, a.H);
-  if (a.dh == 96 && a.dhp == 128) return launch_attn_tc<96, 128>(a, stream);
-  if (a.dh == 64 && a.dhp == 64) return launch_attn_tc<64, 64>(a, stream);
-  if (a.dh == 128 && a.dhp == 128) return launch_attn_tc<128, 128>(a, stream);
-  if (a.dh == 32 && a.dhp == 64) return launch_attn_tc<32, 64>(a, stream);
+  const int kb = a.key_block ? a.key_block : (a.T <= 2048 ? 64 : 128);
+  IEF_CHECK(kb == 64 || kb == 128, "attn_tc: key_block must be 64 or 128");
+#define IEF_ATTN(DH_, DHP_)                                                      \
+  if (a.dh == DH_ && a.dhp == DHP_)                                              \
+    return kb == 64 ? launch_attn_tc<DH_, DHP_, 64>(a, stream) : launch_attn_tc<DH_, DHP_, 128>(a, stream);
+  IEF_ATTN(96, 128)
+  IEF_ATTN(64, 64)
+  IEF_ATTN(128, 128)
+  IEF_ATTN(32, 64)
+#undef IEF_ATTN
   set_error("attn_tc: unsupported head dim %d (padded %d); supported: 32, 64, 96, 128", a.dh, a.dhp);
   return IEFVAD_ERR_INVALID;
 }

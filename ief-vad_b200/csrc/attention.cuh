@@ -12,6 +12,7 @@ struct AttnTcArgs {
   int B = 0, T = 0, H = 0, dh = 0, dhp = 0, Tpad = 0;
   const float* attn_mask = nullptr;    // optional additive [T, T]
   const uint8_t* key_pad = nullptr;    // optional [B, T], non-zero = ignore key
+  int key_block = 0;                   // 0 = heuristic (64 keys per block up to T = 2048, else 128), or 64 / 128
 };
 
 int attn_tc(const AttnTcArgs& a, cudaStream_t stream);

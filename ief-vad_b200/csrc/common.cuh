@@ -215,6 +215,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Same with fp16 (E5M10) operands: a_format = b_format = 0; the tensor pipe runs kind::f16 at the same rate
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 // Shared-memory matrix descriptor for a K-major tile stored as rows of 128 bytes (64 bf16) with the
 // 128-byte swizzle TMA writes (CU_TENSOR_MAP_SWIZZLE_128B): 8-row groups are 1024 B apart (SBO),
 // LBO is unused for swizzled K-major layouts, version = 1 (Blackwell), layout_type = 2 (SWIZZLE_128B).

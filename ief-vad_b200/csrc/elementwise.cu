@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads)
 fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, const float4* __restrict__ lv_i,
             const float4* __restrict__ lv_e, long long n4, float factor, float eps, float4* __restrict__ w_i,
             float4* __restrict__ w_e, float4* __restrict__ fused, bf16* __restrict__ fused_hi,
-            bf16* __restrict__ fused_lo) {
+            bf16* __restrict__ fused_lo, int hi_fp16) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = __ldcs(mu_i + i), b = __ldcs(mu_e + i), c = __ldcs(lv_i + i), d = __ldcs(lv_e + i);
     const float mi[4] = {a.x, a.y, a.z, a.w}, me[4] = {b.x, b.y, b.z, b.w};
@@ -154,7 +154,13 @@ fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, co
     __stcs(w_i + i, make_float4(wi[0], wi[1], wi[2], wi[3]));
     __stcs(w_e + i, make_float4(we[0], we[1], we[2], we[3]));
     if (fused) fused[i] = make_float4(f[0], f[1], f[2], f[3]);
-    if (fused_hi) {
+    if (fused_hi && hi_fp16) {                 // fp16 operand copy (refinement chain of plan H)
+      const __half2 h01 = __floats2half2_rn(f[0], f[1]), h23 = __floats2half2_rn(f[2], f[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&h01);
+      u.y = *reinterpret_cast<const uint32_t*>(&h23);
+      *reinterpret_cast<uint2*>(fused_hi + i * 4) = u;
+    } else if (fused_hi) {
       bf16 h[4], l[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) split_bf16(f[e], h[e], l[e]);
@@ -162,6 +168,12 @@ fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, co
       if (fused_lo) *reinterpret_cast<uint2*>(fused_lo + i * 4) = *reinterpret_cast<uint2*>(l);
     }
   }
+}
+
+__global__ void __launch_bounds__(kThreads)
+to_half_kernel(const float* __restrict__ in, long long n, __half* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(in[i]);
 }
 
 // ---------------------------------------------------------------- classifier: warp-per-row fp32 dot product
@@ -238,7 +250,7 @@ int layernorm(const float* x, long long M, int D, const float* w1, const float* 
 
 int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long n, float factor,
          float eps, float* w_i, float* w_e, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
-         cudaStream_t stream) {
+         cudaStream_t stream, int hi_fp16) {
   IEF_CHECK(n % 4 == 0, "fuse: element count %lld must be a multiple of 4", n);
   if (n == 0) return IEFVAD_OK;
   const long long n4 = n / 4;
@@ -246,7 +258,15 @@ int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* l
       reinterpret_cast<const float4*>(mu_i), reinterpret_cast<const float4*>(mu_e),
       reinterpret_cast<const float4*>(lv_i), reinterpret_cast<const float4*>(lv_e), n4, factor, eps,
       reinterpret_cast<float4*>(w_i), reinterpret_cast<float4*>(w_e), reinterpret_cast<float4*>(fused), fused_hi,
-      fused_lo);
+      fused_lo, hi_fp16);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int to_half(const float* in, long long n, void* out_f16, int num_sms, cudaStream_t stream) {
+  if (n == 0) return IEFVAD_OK;
+  to_half_kernel<<<grid_for(n, num_sms), kThreads, 0, stream>>>(in, n, static_cast<__half*>(out_f16));
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

@@ -16,7 +16,10 @@ int layernorm(const float* x, long long M, int D, const float* w1, const float* 
 // model/imf_vad.py:130-144.  n elements; fused / fused_hi / fused_lo optional.
 int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long n, float factor,
          float eps, float* w_i, float* w_e, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
-         cudaStream_t stream);
+         cudaStream_t stream, int hi_fp16 = 0 /* fused_hi receives fp16 instead of bf16 */);
+
+// fp32 -> fp16 (weights of the fp16-operand refinement GEMMs)
+int to_half(const float* in, long long n, void* out_f16, int num_sms, cudaStream_t stream);
 
 // logits[row] = x[row, :] . w + bias;  scores (optional) = sigmoid(logits)
 int classifier(const float* x, long long M, int D, const float* w, const float* bias, float* logits, float* scores,

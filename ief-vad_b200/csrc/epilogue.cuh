@@ -24,6 +24,7 @@ struct EpiParams {
   bf16* out_hi = nullptr;        // bf16(out)
   bf16* out_lo = nullptr;        // bf16(out - hi), optional
   int ld_bf = 0;
+  int hi_fp16 = 0;               // out_hi receives fp16(out) instead of bf16(out) (tcgen05 path only; no out_lo)
   // EPI_QKV: packed in-projection scattered into the attention kernel's operand layouts
   //   q  [B, H, T, dhp]  (scaled by qscale, columns >= dh never written: kept zero by the allocator)
   //   k  [B, H, T, dhp]

@@ -13,6 +13,7 @@ struct GemmTcArgs {
   int M = 0, N = 0, K = 0;
   int lda = 0, ldw = 0;
   int nsplit = 1;              // 1: plain bf16;  3: hi.hi + hi.lo + lo.hi
+  int fp16 = 0;                // A_hi / W_hi hold fp16 (E5M10) instead of bf16: 8x finer operand rounding, same MMA rate
   int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256 (tests, tuning)
   int force_stages = 0;        // 0 = as many smem stages as fit beside the epilogue buffers (tuning)
   int force_cg = 0;            // 0 = heuristic, 1 = one CTA per tile, 2 = CTA pair (cta_group::2, 256-row tiles)

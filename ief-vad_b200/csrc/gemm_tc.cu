@@ -55,6 +55,8 @@ struct TcEpi {
   int inplace = 0;         // the fp32 output is written over the residual box it was computed from (ring slot)
   uint32_t warp_bytes = 0; // per-warp epilogue smem
   int stages = 4;
+  uint32_t idesc = 0;      // tcgen05 instruction descriptor (operand format bf16 / fp16, tile shape)
+  int hi_fp16 = 0;         // the 16-bit output is fp16 instead of bf16
   // EPI_QKV
   bf16* q = nullptr;
   bf16* k = nullptr;
@@ -183,7 +185,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
+      const uint32_t idesc = ep.idesc;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -370,9 +372,15 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float a = v[g * 8 + 2 * q], b = v[g * 8 + 2 * q + 1];
-            const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
-            hi[q] = pack_bf16x2(ah, bh);
-            lo[q] = pack_bf16x2(a - ah, b - bh);
+            if (ep.hi_fp16) {
+              const __half2 h2 = __floats2half2_rn(a, b);
+              hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[q] = 0u;
+            } else {
+              const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+              hi[q] = pack_bf16x2(ah, bh);
+              lo[q] = pack_bf16x2(a - ah, b - bh);
+            }
           }
           *reinterpret_cast<uint4*>(hb + sw64(lane, g)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (ep.has_lo) *reinterpret_cast<uint4*>(lb + sw64(lane, g)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -467,6 +475,10 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   using Cfg = TcCfg<BN, CG>;
   TcEpi e;
   e.mode = ep.mode; e.bias = ep.bias; e.act = ep.act; e.alpha = ep.alpha; e.split_col = ep.split_col;
+  e.idesc = g.fp16 ? make_idesc_f16(BM * CG, BN) : make_idesc_bf16(BM * CG, BN);
+  e.hi_fp16 = ep.hi_fp16;
+  IEF_CHECK(!g.fp16 || g.nsplit == 1, "gemm_tc: fp16 operands are single-pass (nsplit == 1)");
+  IEF_CHECK(!ep.hi_fp16 || ep.out_lo == nullptr, "gemm_tc: an fp16 output has no lo part");
   TcMaps tm;
   memset(&tm, 0, sizeof(tm));
   if (ep.mode == EPI_ROWMAJOR) {

@@ -94,7 +94,7 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
   IEF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
 
   // ---- carve one fp32 arena (+ bf16 hi / lo arenas mirroring the weight matrices)
-  struct Want { std::string key; long long numel; bool is_weight; float** dst; bf16** hi; bf16** lo; };
+  struct Want { std::string key; long long numel; bool is_weight; float** dst; bf16** hi; bf16** lo; bf16** h16 = nullptr; };
   std::vector<Want> wants;
   const char* mods[2] = {"image", "event"};
   for (int m = 0; m < 2; ++m) {
@@ -136,27 +136,29 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
   for (int i = 0; i < R; ++i) {
     ref1[i].out = ref1[i].in = ref2[i].out = ref2[i].in = D;
     snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.0.weight", i);
-    wants.push_back({buf, 1LL * D * D, true, &ref1[i].w, &ref1[i].w_hi, &ref1[i].w_lo});
+    wants.push_back({buf, 1LL * D * D, true, &ref1[i].w, &ref1[i].w_hi, &ref1[i].w_lo, &ref1[i].w_h16});
     snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.0.bias", i);
     wants.push_back({buf, D, false, &ref1[i].b, nullptr, nullptr});
     snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.2.weight", i);
-    wants.push_back({buf, 1LL * D * D, true, &ref2[i].w, &ref2[i].w_hi, &ref2[i].w_lo});
+    wants.push_back({buf, 1LL * D * D, true, &ref2[i].w, &ref2[i].w_hi, &ref2[i].w_lo, &ref2[i].w_h16});
     snprintf(buf, sizeof(buf), "temporal.refinement_blocks.%d.2.bias", i);
     wants.push_back({buf, D, false, &ref2[i].b, nullptr, nullptr});
   }
   wants.push_back({"temporal.classifier.weight", D, false, &cls_w, nullptr, nullptr});
   wants.push_back({"temporal.classifier.bias", 1, false, &cls_b, nullptr, nullptr});
 
-  size_t f32_elems = 0, bf_elems = 0;
+  size_t f32_elems = 0, bf_elems = 0, h16_elems = 0;
   for (auto& w : wants) {
     f32_elems += align_up(size_t(w.numel), 64);
     if (w.is_weight) bf_elems += align_up(size_t(w.numel), 64);
+    if (w.h16) h16_elems += align_up(size_t(w.numel), 64);
   }
+  IEF_TRY(params_h16.reserve((h16_elems ? h16_elems : 64) * sizeof(bf16)));
   IEF_TRY(params_f32.reserve(f32_elems * sizeof(float)));
   IEF_TRY(params_hi.reserve(bf_elems * sizeof(bf16)));
   IEF_TRY(params_lo.reserve(bf_elems * sizeof(bf16)));
   IEF_CUDA(cudaMemset(params_f32.p, 0, params_f32.bytes));
-  size_t fo = 0, bo = 0;
+  size_t fo = 0, bo = 0, ho = 0;
   for (auto& w : wants) {
     *w.dst = params_f32.as<float>() + fo;
     fo += align_up(size_t(w.numel), 64);
@@ -169,6 +171,11 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
       s.hi = *w.hi;
       s.lo = *w.lo;
       bo += align_up(size_t(w.numel), 64);
+    }
+    if (w.h16) {
+      *w.h16 = params_h16.as<bf16>() + ho;
+      s.h16 = *w.h16;
+      ho += align_up(size_t(w.numel), 64);
     }
     slots[w.key] = s;
   }
@@ -201,6 +208,7 @@ int Model::set_param(const char* key, const float* dptr, long long numel, cudaSt
   IEF_CHECK(s.numel == numel, "parameter '%s': expected %lld elements, got %lld", key, s.numel, numel);
   IEF_CUDA(cudaMemcpyAsync(s.dst, dptr, size_t(numel) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   if (s.hi) IEF_TRY(ingest(s.dst, IEFVAD_DT_F32, numel, nullptr, s.hi, s.lo, num_sms, stream));
+  if (s.h16) IEF_TRY(to_half(s.dst, numel, s.h16, num_sms, stream));
   s.loaded = true;
   return IEFVAD_OK;
 }
@@ -288,7 +296,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           GemmTcArgs g1;
           g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = ip.w_hi; g1.W_lo = ip.w_lo;
           g1.M = int(M); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1;
-          IEF_PROF(KC_GEMM_TC, 6.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
+          IEF_PROF(KC_GEMM_QKV, 6.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
           AttnTcArgs at;
           at.q = qb.as<bf16>(); at.k = kb.as<bf16>(); at.vt = vtb.as<bf16>(); at.out = h_hi.as<bf16>(); at.ldo = D;
           at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
@@ -297,7 +305,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           e2.bias = op.b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.out_f32 = y32.as<float>(); e2.ld_f32 = D;
           GemmTcArgs g2;
           g2.A_hi = h_hi.as<bf16>(); g2.W_hi = op.w_hi; g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
-          IEF_PROF(KC_GEMM_TC, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
+          IEF_PROF(KC_GEMM_OUT, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
           // LN_i (+ whitening LN after the last layer, :117/:123); bf16 hi(/lo) feed the next GEMM
           const bool need_lo = last ? (plan & PLAN_SPLIT_HEADS) != 0 : sp;
           IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
@@ -323,16 +331,17 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
         gh.A_hi = a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>(); gh.W_hi = heads[m].w_hi; gh.W_lo = heads[m].w_lo;
         gh.M = int(M); gh.N = 2 * D; gh.K = D; gh.lda = D; gh.ldw = D;
         gh.nsplit = (plan & PLAN_SPLIT_HEADS) ? 3 : 1;
-        IEF_PROF(KC_GEMM_TC, 4.0 * M * D * D, gemm_tc(gh, eh, num_sms, stream));
+        IEF_PROF(KC_GEMM_HEADS, 4.0 * M * D * D, gemm_tc(gh, eh, num_sms, stream));
       }
     }
     // uncertainty-weighted fusion (:130-144)
-    const bool rsp = !fp32_plan && (plan & PLAN_SPLIT_REFINE);
+    const bool r16 = !fp32_plan && (plan & PLAN_FP16_REFINE);             // fp16 single-pass refinement operands
+    const bool rsp = !fp32_plan && !r16 && (plan & PLAN_SPLIT_REFINE);
     float* fused_out = fused + row0 * D;
     float* xcur = (R == 0) ? fused_out : x32.as<float>();
     IEF_PROF(KC_FUSE, double(M) * D * 28, fuse(image_mu + row0 * D, event_mu + row0 * D, image_logvar + row0 * D, event_logvar + row0 * D, M * D,
                  factor, eps, w_i + row0 * D, w_e + row0 * D, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
-                 (rsp && R > 0) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+                 (rsp && R > 0) ? a_lo.as<bf16>() : nullptr, num_sms, stream, r16 ? 1 : 0));
     // iterative refinement (:146-149): x <- x - lambda * (W2 relu(W1 x + b1) + b2)
     for (int i = 0; i < R; ++i) {
       const bool last = (i == R - 1);
@@ -348,19 +357,19 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       } else {
         EpiParams e1;
         e1.bias = ref1[i].b; e1.act = ACT_RELU; e1.out_hi = h_hi.as<bf16>(); e1.out_lo = rsp ? h_lo.as<bf16>() : nullptr;
-        e1.ld_bf = D;
+        e1.ld_bf = D; e1.hi_fp16 = r16 ? 1 : 0;
         GemmTcArgs g1;
-        g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = ref1[i].w_hi; g1.W_lo = ref1[i].w_lo;
-        g1.M = int(M); g1.N = D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = rsp ? 3 : 1;
-        IEF_PROF(KC_GEMM_TC, 2.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
+        g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = r16 ? ref1[i].w_h16 : ref1[i].w_hi; g1.W_lo = ref1[i].w_lo;
+        g1.M = int(M); g1.N = D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = rsp ? 3 : 1; g1.fp16 = r16 ? 1 : 0;
+        IEF_PROF(KC_GEMM_REF1, 2.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
         EpiParams e2;
         e2.bias = ref2[i].b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.alpha = -lambda_ref;
         e2.out_f32 = xnext; e2.ld_f32 = D;
-        if (!last) { e2.out_hi = a_hi.as<bf16>(); e2.out_lo = rsp ? a_lo.as<bf16>() : nullptr; e2.ld_bf = D; }
+        if (!last) { e2.out_hi = a_hi.as<bf16>(); e2.out_lo = rsp ? a_lo.as<bf16>() : nullptr; e2.ld_bf = D; e2.hi_fp16 = r16 ? 1 : 0; }
         GemmTcArgs g2;
-        g2.A_hi = h_hi.as<bf16>(); g2.A_lo = h_lo.as<bf16>(); g2.W_hi = ref2[i].w_hi; g2.W_lo = ref2[i].w_lo;
-        g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D; g2.nsplit = rsp ? 3 : 1;
-        IEF_PROF(KC_GEMM_TC, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
+        g2.A_hi = h_hi.as<bf16>(); g2.A_lo = h_lo.as<bf16>(); g2.W_hi = r16 ? ref2[i].w_h16 : ref2[i].w_hi; g2.W_lo = ref2[i].w_lo;
+        g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D; g2.nsplit = rsp ? 3 : 1; g2.fp16 = r16 ? 1 : 0;
+        IEF_PROF(KC_GEMM_REF2, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
       }
     }
     // classifier (:150) stays fp32 in every plan
@@ -370,7 +379,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
 }
 
 void Model::destroy() {
-  DevBuf* all[] = {&params_f32, &params_hi, &params_lo, &x32, &y32, &a_hi, &a_lo, &h_hi, &h_lo,
+  DevBuf* all[] = {&params_f32, &params_hi, &params_lo, &params_h16, &x32, &y32, &a_hi, &a_lo, &h_hi, &h_lo,
                    &qb, &kb, &vtb, &qkv32, &attn32, &h32};
   for (DevBuf* b : all) b->release();
 }

@@ -14,7 +14,9 @@ namespace iefvad {
 
 // precision plan: -1 = every contraction in fp32 FFMA; otherwise a bit mask of which bf16 GEMM groups use the
 // 3-term split (A_hi.W_hi + A_hi.W_lo + A_lo.W_hi)
-enum : int { PLAN_FP32 = -1, PLAN_SPLIT_ENCODER = 1, PLAN_SPLIT_HEADS = 2, PLAN_SPLIT_REFINE = 4 };
+// PLAN_FP16_REFINE: the refinement Linears take fp16 (E5M10) operands in a single MMA pass instead of the 3-term bf16
+// split - the same 8.5e-5 score error at a third of the MMA work
+enum : int { PLAN_FP32 = -1, PLAN_SPLIT_ENCODER = 1, PLAN_SPLIT_HEADS = 2, PLAN_SPLIT_REFINE = 4, PLAN_FP16_REFINE = 8 };
 
 struct DevBuf {
   void* p = nullptr;
@@ -29,6 +31,7 @@ struct Linear {          // y = x W^T + b, W [out, in]
   float* b = nullptr;
   bf16* w_hi = nullptr;
   bf16* w_lo = nullptr;
+  bf16* w_h16 = nullptr;  // fp16 copy (16-bit storage), refinement Linears only
   int out = 0, in = 0;
 };
 
@@ -37,13 +40,14 @@ struct ParamSlot {
   long long numel = 0;
   bf16* hi = nullptr;    // packed copies refreshed on upload (weights only)
   bf16* lo = nullptr;
+  bf16* h16 = nullptr;   // fp16 copy (refinement weights)
   bool loaded = false;
 };
 
 struct Model {
   int D = 0, H = 0, L = 0, R = 0, dh = 0, dhp = 0;
   float lambda_ref = 0.5f, factor = 1.f, eps = 1e-8f;
-  int plan = PLAN_SPLIT_HEADS | PLAN_SPLIT_REFINE;
+  int plan = PLAN_SPLIT_HEADS | PLAN_FP16_REFINE;
   long long max_rows = 32768;    // rows per internal slab (whole batch elements)
   int num_sms = 148;
   int device = 0;
@@ -59,7 +63,7 @@ struct Model {
   float* cls_b = nullptr;
 
   std::unordered_map<std::string, ParamSlot> slots;
-  DevBuf params_f32, params_hi, params_lo;
+  DevBuf params_f32, params_hi, params_lo, params_h16;
 
   // workspace (one slab)
   DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32;
@@ -77,8 +81,8 @@ struct Model {
 };
 
 // Per-kernel-class device timing (CUDA events on the launching stream) for bench.py's roofline block.
-enum : int { KC_GEMM_TC = 0, KC_ATTN_TC, KC_LAYERNORM, KC_FUSE, KC_CLASSIFIER, KC_INGEST, KC_GEMM_SIMT, KC_ATTN_SIMT,
-             KC_COUNT };
+enum : int { KC_GEMM_QKV = 0, KC_ATTN_TC, KC_LAYERNORM, KC_FUSE, KC_CLASSIFIER, KC_INGEST, KC_GEMM_SIMT, KC_ATTN_SIMT,
+             KC_GEMM_OUT, KC_GEMM_HEADS, KC_GEMM_REF1, KC_GEMM_REF2, KC_COUNT };
 struct Profiler {
   bool on = false;
   struct Rec { int cls; double work; cudaEvent_t a, b; };   // work = algorithmic flops (GEMM/attn) or bytes (others)

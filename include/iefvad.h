@@ -40,8 +40,10 @@ extern "C" {
 #define IEFVAD_PLAN_SPLIT_ENCODER 1
 #define IEFVAD_PLAN_SPLIT_HEADS 2
 #define IEFVAD_PLAN_SPLIT_REFINE 4
+#define IEFVAD_PLAN_FP16_REFINE 8 /* refinement Linears: fp16 (E5M10) operands, one MMA pass, fp32 accumulate */
 #define IEFVAD_PLAN_A (IEFVAD_PLAN_SPLIT_HEADS)
-#define IEFVAD_PLAN_B (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_SPLIT_REFINE) /* default */
+#define IEFVAD_PLAN_B (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_SPLIT_REFINE) /* bf16 operands everywhere */
+#define IEFVAD_PLAN_H (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_FP16_REFINE)  /* default: same error as B, 1/3 of its refinement MMAs */
 
 int iefvad_abi_version(void);
 const char* iefvad_last_error(void);
@@ -204,9 +206,12 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stage
 uint64_t iefvad_launch_count(void);
 
 /* Per-kernel-class device timing of the model forward with CUDA events on the launching stream.
- * classes: 0 gemm_tc, 1 attn_tc, 2 layernorm, 3 fuse, 4 classifier, 5 ingest, 6 gemm_simt, 7 attn_simt.
- * iefvad_profile_read synchronises, fills ms / work (algorithmic FLOPs for classes 0, 1, 6, 7; algorithmic bytes
- * otherwise) / launches (arrays of 8) for everything recorded since the last read, and clears the record. */
+ * classes (IEFVAD_PROFILE_CLASSES = 12): 0 gemm_tc QKV in-projection, 1 attn_tc, 2 layernorm, 3 fuse, 4 classifier,
+ * 5 ingest, 6 gemm_simt, 7 attn_simt, 8 gemm_tc out-projection, 9 gemm_tc heads, 10 gemm_tc refinement Linear 1
+ * (ReLU), 11 gemm_tc refinement Linear 2 (residual).  iefvad_profile_read synchronises, fills ms / work (algorithmic
+ * FLOPs for the GEMM and attention classes, algorithmic bytes otherwise) / launches (arrays of 12) for everything
+ * recorded since the last read, and clears the record. */
+#define IEFVAD_PROFILE_CLASSES 12
 int iefvad_profile_enable(int on);
 int iefvad_profile_read(double* ms, double* work, int64_t* launches);
 

@@ -13,8 +13,8 @@ from oracle import iefvad_oracle as O
 pytestmark = pytest.mark.gpu
 
 OUT_KEYS = ["fused", "logits", "image_mu", "event_mu", "image_logvar", "event_logvar", "w_i", "w_e"]
-SCORE_TOL = {"fp32": 1e-5, "B": 1e-3, "A": 1e-3, "split": 1e-3}
-TENSOR_TOL = {"fp32": 2e-5, "B": 1e-3, "A": 2e-3, "split": 1e-3}
+SCORE_TOL = {"fp32": 1e-5, "B": 1e-3, "A": 1e-3, "split": 1e-3, "H": 1e-3}
+TENSOR_TOL = {"fp32": 2e-5, "B": 1e-3, "A": 2e-3, "split": 1e-3, "H": 1e-3}
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +39,7 @@ def _small_model(pkg, z):
 
 
 @pytest.mark.parametrize("name", ["small_studentt", "small_gaussian", "small_r0"])
-@pytest.mark.parametrize("plan", ["fp32", "B", "A"])
+@pytest.mark.parametrize("plan", ["fp32", "B", "A", "H"])
 def test_small_models_all_eight_tensors(pkg, name, plan):
     z = load_golden(name + ".npz")
     m = _small_model(pkg, z)
@@ -72,7 +72,7 @@ def full(pkg):
 
 
 @pytest.mark.parametrize("tag", ["full_default", "full_perturbed"])
-@pytest.mark.parametrize("plan", ["fp32", "B", "A"])
+@pytest.mark.parametrize("plan", ["fp32", "B", "A", "H"])
 def test_full_size_c1_against_reference_golden(pkg, full, tag, plan):
     _, synth = pkg
     m, z = full[tag]
@@ -90,7 +90,7 @@ def test_full_size_c1_against_reference_golden(pkg, full, tag, plan):
         assert e < TENSOR_TOL[plan], (k, e)
 
 
-@pytest.mark.parametrize("plan", ["fp32", "B"])
+@pytest.mark.parametrize("plan", ["fp32", "B", "H"])
 def test_full_size_ragged_chunked_and_long(pkg, full, plan):
     _, synth = pkg
     m, z = full["full_perturbed"]
@@ -118,7 +118,7 @@ def test_batch_invariance_and_slabbing_bit_exact(pkg, full):
     iefvad_b200, synth = pkg
     from iefvad_b200 import _lib
     m, _ = full["full_default"]
-    m.temporal.precision = "B"
+    m.temporal.precision = "H"
     img, ev = synth.make_video(30, 1100)
     ci, ce = synth.chunk_video(img).cuda(), synth.chunk_video(ev).cuda()
     with torch.no_grad():
@@ -134,7 +134,7 @@ def test_batch_invariance_and_slabbing_bit_exact(pkg, full):
 def test_input_dtypes_and_errors(pkg, full):
     iefvad_b200, synth = pkg
     m, _ = full["full_default"]
-    m.temporal.precision = "B"
+    m.temporal.precision = "H"
     img, ev = synth.make_video(0, 64)
     with torch.no_grad():
         a = m(img[None].cuda(), ev[None].cuda(), None, None, None)["logits"]
@@ -164,7 +164,7 @@ def test_input_dtypes_and_errors(pkg, full):
 def test_load_state_dict_refreshes_device_weights(pkg, full):
     iefvad_b200, synth = pkg
     m, z = full["full_default"]
-    m.temporal.precision = "B"
+    m.temporal.precision = "H"
     img, ev = synth.make_video(0, 256)
     with torch.no_grad():
         base = m(img[None].cuda(), ev[None].cuda(), None, None, None)["logits"].clone()
