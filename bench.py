@@ -62,6 +62,8 @@ class ClockSampler:
         self.nvml = None
         self.samples = []
         self._stop = threading.Event()
+        self.recording = False        # start() runs ahead of the warm-up (NVML init stalls the driver for tens of ms);
+                                      # only samples taken while `recording` (the timed region) are kept
 
     def _nvml_loop(self):
         n = self.nvml
@@ -75,7 +77,8 @@ class ClockSampler:
                 sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
                 mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
                 r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, mx, [k for k, b in bits.items() if r & b]))
+                if self.recording:
+                    self.samples.append((sm, mx, [k for k, b in bits.items() if r & b]))
             except Exception:
                 pass
             self._stop.wait(0.05)
@@ -107,7 +110,8 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            if self.recording:
+                self.lines.append(line.strip())
 
     def stop(self):
         if self.nvml is not None:
@@ -280,13 +284,15 @@ def main():
     with torch.no_grad():
         # ---- device-resident run (value)
         evaluator.set_device_features(img_c, ev_c)
-        for _ in range(max(3, args.warmup)):
-            evaluator.step()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(max(3, args.warmup)):
+            evaluator.step()
         l0 = _lib.lib.iefvad_launch_count()
+        sampler.recording = True
         ms_dev, res = timed(False, args.steps)
+        sampler.recording = False
         launches = _lib.lib.iefvad_launch_count() - l0
         clocks = sampler.stop() if rank == 0 else None
         # ---- end-to-end run (pinned host inputs, H2D inside the timed region)

@@ -339,7 +339,7 @@ int iefvad_transformer(const float* x, const float* const* params, int layers, i
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,
                       float* ms_per_iter) {
   IEF_CHECK(M > 0 && M < (1LL << 31) && N > 0 && K > 0 && iters > 0 && ms_per_iter, "iefvad_bench_gemm: bad argument");
-  IEF_CHECK(epi_kind >= 0 && epi_kind <= 4, "iefvad_bench_gemm: epi_kind in [0, 4]");
+  IEF_CHECK(epi_kind >= 0 && epi_kind <= 6, "iefvad_bench_gemm: epi_kind in [0, 6]");
   int sms = 0;
   IEF_TRY(current_sms(&sms));
   cudaStream_t st = nullptr;
@@ -371,6 +371,11 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stage
     ep.out_hi = (bf16*)oh; ep.out_lo = (bf16*)ol; ep.ld_bf = N;
   }
   if (epi_kind == 3) { ep.act = ACT_RELU; ep.out_hi = (bf16*)oh; ep.out_lo = (bf16*)ol; ep.ld_bf = N; }
+  if (epi_kind == 5) { ep.act = ACT_RELU; ep.out_hi = (bf16*)oh; ep.ld_bf = N; ep.hi_fp16 = 1; }
+  if (epi_kind == 6) {
+    ep.resid = (float*)resid; ep.ld_resid = N; ep.alpha = -0.5f; ep.out_f32 = (float*)of; ep.ld_f32 = N;
+    ep.out_hi = (bf16*)oh; ep.ld_bf = N; ep.hi_fp16 = 1;
+  }
   if (epi_kind == 4) {
     IEF_CHECK(N % (3 * H * 32) == 0 && M % T == 0, "iefvad_bench_gemm: qkv epilogue needs N = 3*8*dh, M %% 256 == 0");
     IEF_TRY(sc.get(&q, size_t(M) * H * dhp * 2));
@@ -384,6 +389,7 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stage
   g.M = int(M); g.N = N; g.K = K; g.lda = K; g.ldw = K; g.nsplit = nsplit; g.force_stages = stages;
   g.force_bn = tile_n == 512 ? 256 : tile_n;
   g.force_cg = tile_n == 512 ? 2 : (tile_n ? 1 : 0);
+  g.fp16 = (epi_kind >= 5) ? 1 : 0;
   for (int i = 0; i < 3; ++i) IEF_TRY(gemm_tc(g, ep, sms, st));
   cudaEvent_t e0, e1;
   IEF_CUDA(cudaEventCreate(&e0));

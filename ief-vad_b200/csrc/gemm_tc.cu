@@ -4,13 +4,14 @@
 // :125-128 heads, :148 refinement MLPs) - K-major A (activations) and K-major W (nn.Linear stores
 // [out, in]) are exactly the layouts UMMA wants, so no transposes anywhere.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0     TMA producer   : cp.async.bulk.tensor 128x64 (A) and BNx64 (W) bf16 boxes, 128B swizzle,
 //                               into a smem ring guarded by full/empty mbarriers
 //   warp 1     MMA issuer     : one thread issues 4 x tcgen05.mma (128 x BN x 16) per k-block into one of two
 //                               TMEM accumulator buffers; tcgen05.commit releases smem slots / publishes tiles
-//   warps 2-5  epilogue       : each warp owns 32 accumulator rows (its TMEM lane quarter) and walks them in
-//                               32-column chunks: tcgen05.ld (thread == row) -> bias / activation / residual /
+//   warps 2-9  epilogue       : each warp owns 32 accumulator rows (its TMEM lane quarter; two warps per quarter take
+//                               the even / odd chunks so that every scheduler has two warps to interleave) and
+//                               walks them in 32-column chunks: tcgen05.ld (thread == row) -> bias / activation / residual /
 //                               bf16 hi+lo split in registers -> swizzled per-warp smem boxes -> TMA bulk tensor
 //                               stores.  The fp32 residual arrives the same way (TMA loads into a per-warp ring,
 //                               prefetched several chunks - and across tile boundaries - ahead), so no epilogue
@@ -40,7 +41,9 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxResidSlots = 4;
 constexpr uint32_t kF32Box = 32 * CW * 4;     // one 32-row x 32-col fp32 box (128-byte rows, SWIZZLE_128B)
 constexpr uint32_t kBfBox = 32 * CW * 2;      // the same box in bf16 (64-byte rows, SWIZZLE_64B)
-constexpr uint32_t kBarBytes = 512;
+constexpr uint32_t kBarBytes = 768;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter: one takes the even, one the odd column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kSmemLimit = 232448;       // 227 KB opt-in maximum per CTA on sm_100
 
 // everything the device epilogue needs besides the tensor maps
@@ -97,20 +100,20 @@ __device__ __forceinline__ uint32_t sw64(int row, int g) { return uint32_t(row) 
 // leader CTA issues MMAs; its commits multicast to the mbarriers of both CTAs; both producers signal the leader's
 // `full` barrier; both epilogues arrive on the leader's `tempty`.
 template <int BN, int MODE, int ACT, int CG>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nsplit, const TcEpi ep) {
   using Cfg = TcCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = ep.stages;
   uint8_t* epi_base = smem + size_t(STAGES) * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + 4 * ep.warp_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + kEpiWarps * ep.warp_bytes);
   uint64_t* full = bars;
   uint64_t* empty = full + kMaxStages;
   uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* rfull_all = tempty + 2;                                  // [4 warps][kMaxResidSlots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_all + 4 * kMaxResidSlots);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_all + kEpiWarps * kMaxResidSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,9 +138,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4 * CG);       // the epilogue warps of every CTA of the pair arrive on the leader's
+      mbar_init(&tempty[s], kEpiWarps * CG);      // the epilogue warps of every CTA of the pair arrive on the leader's
     }
-    for (int s = 0; s < 4 * kMaxResidSlots; ++s) mbar_init(&rfull_all[s], 1);
+    for (int s = 0; s < kEpiWarps * kMaxResidSlots; ++s) mbar_init(&rfull_all[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -215,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;         // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int par = (warp - 2) >> 2;      // the two warps of a quarter split the column chunks: c = par, par + 2, ...
     uint8_t* wb = epi_base + size_t(warp - 2) * ep.warp_bytes;
     uint8_t* Rb = wb;                                                      // [nr] fp32 residual (/ in-place output) boxes
     uint8_t* Ob = Rb + size_t(ep.nr) * kF32Box;                            // [2] fp32 output boxes (no residual ring)
@@ -224,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     const bool discard = ep.mode == EPI_DISCARD;
 
     // residual prefetch cursor (lane 0): walks the same (tile, chunk) sequence as the consumer, ahead of it
-    int pf_tile = tile0, pf_c = 0;
+    int pf_tile = tile0, pf_c = par;
     uint32_t pf_n = 0;
     auto chunks_of = [&](int tile) {
       const int n_blk = tile % num_n;
@@ -238,8 +242,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       mbar_arrive_expect_tx(&rfull[slot], kF32Box);
       tma_load_2d(&tm.r, &rfull[slot], Rb + size_t(slot) * kF32Box, n_blk * BN + pf_c * CW, m_blk * BM + quarter * 32);
       ++pf_n;
-      if (++pf_c == chunks_of(pf_tile)) { pf_c = 0; pf_tile += tile_step; }
+      pf_c += 2;
+      while (pf_tile < num_tiles && pf_c >= chunks_of(pf_tile)) { pf_c = par; pf_tile += tile_step; }
     };
+    while (pf_tile < num_tiles && pf_c >= chunks_of(pf_tile)) pf_tile += tile_step;   // tiles too narrow for this parity
     if (ep.has_resid && lane == 0) {
       tma_prefetch_desc(&tm.r);
       for (int i = 0; i < ep.nr; ++i) prefetch_resid();
@@ -275,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
         for (int g = 0; g < 8; ++g) {
           v[g * 4 + 0] += bnext[g].x; v[g * 4 + 1] += bnext[g].y; v[g * 4 + 2] += bnext[g].z; v[g * 4 + 3] += bnext[g].w;
         }
-        if (c + 1 < nchunks) fetch_bias(col0 + CW);
+        if (c + 2 < nchunks) fetch_bias(col0 + 2 * CW);
       }
       if (ACT != ACT_NONE) {
 #pragma unroll
@@ -407,7 +413,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       const uint32_t aph = (it >> 1) & 1;
       nchunks = chunks_of(tile);
       row0 = m_blk * BM + quarter * 32;               // first row of this warp; this thread owns row0 + lane
-      if (!discard) fetch_bias(n_blk * BN);           // in flight while the accumulator is still being produced
+      if (!discard && par < nchunks) fetch_bias(n_blk * BN + par * CW);   // in flight while the accumulator is produced
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + uint32_t(as * BN) + (uint32_t(quarter * 32) << 16);
@@ -419,15 +425,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
           else mbar_arrive(&tempty[as]);
         }
       };
-      // the tcgen05.ld of chunk c + 1 is in flight (into vn) while chunk c is processed (in v)
+      // the tcgen05.ld of this warp's next chunk is in flight (into vn) while the current one is processed (in v)
       float v[32], vn[32];
-      tmem_ld32(t0, vn);
+      if (par >= nchunks) { release_tmem(); continue; }
+      tmem_ld32(t0 + uint32_t(par * CW), vn);
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = par; c < nchunks; c += 2) {
         tmem_ld_wait_for(vn);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = vn[j];
-        if (c + 1 < nchunks) tmem_ld32(t0 + uint32_t((c + 1) * CW), vn);
+        if (c + 2 < nchunks) tmem_ld32(t0 + uint32_t((c + 2) * CW), vn);
         else release_tmem();
         if (!discard) process(v, c);
       }
@@ -455,7 +462,7 @@ int launch_inst(const TcMaps& tm, const GemmTcArgs& g, const TcEpi& e, int grid,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -502,10 +509,10 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   // per-warp epilogue smem: a residual ring whose slots double as the fp32 output boxes (in place), else two fp32
   // output boxes; bf16 boxes always ping-pong
   e.inplace = (e.has_resid && e.has_f32) ? 1 : 0;
-  e.nr = e.has_resid ? ((e.has_hi && e.inplace) ? 3 : 4) : 0;
+  e.nr = e.has_resid ? (e.has_lo ? 2 : 3) : 0;      // the widest epilogue (fp32 + hi + lo) trades ring depth for a stage
   e.warp_bytes = e.nr * kF32Box + ((e.has_f32 && !e.inplace) ? 2 * kF32Box : 0) + (e.has_hi ? 2 * kBfBox : 0) +
                  (e.has_lo ? 2 * kBfBox : 0);
-  const uint32_t fixed = 1024 + 4 * e.warp_bytes + kBarBytes;
+  const uint32_t fixed = 1024 + kEpiWarps * e.warp_bytes + kBarBytes;
   int stages = int((kSmemLimit - fixed) / Cfg::kStageBytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (g.force_stages > 0 && g.force_stages < stages) stages = g.force_stages;

@@ -48,7 +48,7 @@ struct Model {
   int D = 0, H = 0, L = 0, R = 0, dh = 0, dhp = 0;
   float lambda_ref = 0.5f, factor = 1.f, eps = 1e-8f;
   int plan = PLAN_SPLIT_HEADS | PLAN_FP16_REFINE;
-  long long max_rows = 32768;    // rows per internal slab (whole batch elements)
+  long long max_rows = 262144;   // rows per internal slab (whole batch elements); ~18 KB of workspace per row
   int num_sms = 148;
   int device = 0;
 

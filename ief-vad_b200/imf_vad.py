@@ -87,6 +87,9 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
                 h, int(self.embed_dim), int(self.num_heads), int(self.num_layers), int(self.num_refinement_steps),
                 float(self.lambda_ref), _lib.NOISE[self.noise_model], float(self.nu), float(self.epsilon)))
         self._handle, self._handle_device = h.value, device
+        max_rows = int(os.environ.get("IEFVAD_MAX_ROWS", "0") or 0)          # rows per internal slab (tuning knob)
+        if max_rows > 0:
+            _lib.check(_lib.lib.iefvad_model_set_max_rows(self._handle, max_rows))
         return self._handle
 
     def _sync_params(self, handle: int, device: torch.device, stream: int) -> None:

@@ -66,7 +66,7 @@ int iefvad_model_set_param(iefvad_model* m, const char* key, const float* data, 
 
 int iefvad_model_set_plan(iefvad_model* m, int plan);
 int iefvad_model_get_plan(const iefvad_model* m);
-/* rows per internal slab (bounds the activation workspace); default 32768 */
+/* rows per internal slab (bounds the activation workspace, ~18 KB per row); default 262144 */
 int iefvad_model_set_max_rows(iefvad_model* m, int64_t max_rows);
 
 /* Replaces MMFMIL.forward(img_visual, ev_visual, padding_mask, text, lengths), model/imf_vad.py:40-44 ->
@@ -197,7 +197,8 @@ int iefvad_transformer(const float* x, const float* const* params, int layers, i
 
 /* Micro-benchmark of the tcgen05 GEMM on library-allocated buffers (synchronises; default stream): M x N x K,
  * nsplit 1 | 3, tile_n 0 | 64 | 128 | 256 | 512 (as for iefvad_linear), stages 0 (= as many as fit) or a cap on the operand ring depth, epi_kind 0 = mainloop only (discard), 1 = fp32 out, 2 = refinement
- * epilogue (fp32 residual in, fp32 + bf16 hi/lo out), 3 = ReLU -> bf16 hi/lo, 4 = QKV scatter.  Writes the mean
+ * epilogue (fp32 residual in, fp32 + bf16 hi/lo out), 3 = ReLU -> bf16 hi/lo, 4 = QKV scatter, 5 = fp16 operands,
+ * ReLU -> fp16, 6 = fp16 operands, fp32 residual in, fp32 + fp16 out (the two refinement Linears of plan H).  Writes the mean
  * device time of `iters` back-to-back launches (CUDA events). */
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,
                       float* ms_per_iter);
