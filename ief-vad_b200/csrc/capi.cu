@@ -20,7 +20,11 @@ using namespace iefvad;
 
 struct iefvad_model {
   Model impl;
-  DevBuf host_in[2], host_out[7], host_logits, host_scores;   // scratch of iefvad_model_forward_host
+  // scratch of the host-input forward: ping-pong input buffers filled on a copy stream while the previous part computes
+  DevBuf host_in[2][2], host_out[7], host_logits, host_scores;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_start = nullptr;
+  int64_t host_part_rows = 32768;
 };
 
 namespace {
@@ -72,8 +76,14 @@ int iefvad_model_create(iefvad_model** out, int embed_dim, int num_heads, int nu
 void iefvad_model_destroy(iefvad_model* m) {
   if (!m) return;
   m->impl.destroy();
-  for (auto& b : m->host_in) b.release();
+  for (auto& pp : m->host_in) for (auto& b : pp) b.release();
   for (auto& b : m->host_out) b.release();
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (m->ev_copied[i]) cudaEventDestroy(m->ev_copied[i]);
+    if (m->ev_consumed[i]) cudaEventDestroy(m->ev_consumed[i]);
+  }
+  if (m->ev_start) cudaEventDestroy(m->ev_start);
   m->host_logits.release();
   m->host_scores.release();
   delete m;
@@ -108,38 +118,99 @@ int iefvad_model_forward(iefvad_model* m, const void* img, const void* ev, int i
                          w_e, scores, static_cast<cudaStream_t>(stream));
 }
 
-int iefvad_model_forward_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
-                              int64_t T, float* logits_host, float* scores_host, void* stream) {
-  IEF_CHECK(m && img_host && ev_host && logits_host, "iefvad_model_forward_host: null argument");
+// Host-input forward, pipelined: the batch is cut into parts of whole batch elements; part p + 1 travels host -> device
+// on the library's copy stream into the other input buffer while part p computes on the caller's stream, so only the
+// first part's copy is exposed (the copy engine outruns the forward: ~18 k rows/ms over PCIe vs ~12 k rows/ms).
+static int forward_from_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
+                             int64_t T, float* logits_host, float* scores_host, float* logits_dev, float* scores_dev,
+                             cudaStream_t st) {
+  IEF_CHECK(m && img_host && ev_host, "host-input forward: null argument");
   IEF_CHECK(in_dtype >= 0 && in_dtype <= 2, "unsupported input dtype code %d", in_dtype);
   IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (B == 0 || T == 0) return IEFVAD_OK;
   const int D = m->impl.D;
   const size_t es = (in_dtype == IEFVAD_F32) ? 4 : 2;
-  int64_t slabB = m->impl.max_rows / T;
-  if (slabB < 1) slabB = 1;
-  if (slabB > B) slabB = B;
-  const size_t rows = size_t(slabB) * T;
-  for (auto& b : m->host_in) IEF_TRY(b.reserve(rows * D * es));
+  // Part sizes grow geometrically (x 1.4, the copy engine's lead over the forward) from host_part_rows / 4: a small
+  // first part keeps the exposed copy short, large later parts keep the GEMM grids full.
+  const int64_t cap_rows = m->impl.max_rows;
+  std::vector<int64_t> partsB;
+  {
+    double want = double(m->host_part_rows) / 4.0;
+    int64_t left = B;
+    while (left > 0) {
+      int64_t pb = int64_t(want / double(T));
+      if (pb < 1) pb = 1;
+      if (pb * T > cap_rows) pb = cap_rows / T > 0 ? cap_rows / T : 1;
+      if (pb > left || left - pb < pb / 4) pb = left;      // fold a small tail into the last part
+      if (pb * T > cap_rows && left > pb) pb = left;         // (keeps the invariant below simple)
+      partsB.push_back(pb);
+      left -= pb;
+      want *= 1.4;
+    }
+  }
+  int64_t maxB = 0;
+  for (int64_t pb : partsB) maxB = pb > maxB ? pb : maxB;
+  const size_t rows = size_t(maxB) * T;
+  if (!m->copy_stream) {
+    IEF_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      IEF_CUDA(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+      IEF_CUDA(cudaEventCreateWithFlags(&m->ev_consumed[i], cudaEventDisableTiming));
+    }
+    IEF_CUDA(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+  }
+  for (auto& pp : m->host_in) for (auto& b : pp) IEF_TRY(b.reserve(rows * D * es));
   for (auto& b : m->host_out) IEF_TRY(b.reserve(rows * D * 4));
-  IEF_TRY(m->host_logits.reserve(rows * 4));
-  IEF_TRY(m->host_scores.reserve(rows * 4));
-  for (int64_t b0 = 0; b0 < B; b0 += slabB) {
-    const int64_t Bs = (B - b0 < slabB) ? (B - b0) : slabB;
+  if (!logits_dev) IEF_TRY(m->host_logits.reserve(size_t(B) * T * 4));
+  if (!scores_dev && scores_host) IEF_TRY(m->host_scores.reserve(size_t(B) * T * 4));
+  float* ldev = logits_dev ? logits_dev : m->host_logits.as<float>();
+  float* sdev = scores_dev ? scores_dev : (scores_host ? m->host_scores.as<float>() : nullptr);
+  cudaStream_t cs = m->copy_stream;
+  // the copy stream must not run ahead of work already queued on the caller's stream that still reads the buffers
+  IEF_CUDA(cudaEventRecord(m->ev_start, st));
+  IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_start, 0));
+  int64_t b0 = 0;
+  for (int p = 0; p < int(partsB.size()); b0 += partsB[p], ++p) {
+    const int buf = p & 1;
+    const int64_t Bs = partsB[p];
     const size_t r0 = size_t(b0) * T, nr = size_t(Bs) * T;
-    IEF_CUDA(cudaMemcpyAsync(m->host_in[0].p, static_cast<const uint8_t*>(img_host) + r0 * D * es, nr * D * es,
-                             cudaMemcpyHostToDevice, st));
-    IEF_CUDA(cudaMemcpyAsync(m->host_in[1].p, static_cast<const uint8_t*>(ev_host) + r0 * D * es, nr * D * es,
-                             cudaMemcpyHostToDevice, st));
+    if (p >= 2) IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_consumed[buf], 0));
+    IEF_CUDA(cudaMemcpyAsync(m->host_in[buf][0].p, static_cast<const uint8_t*>(img_host) + r0 * D * es, nr * D * es,
+                             cudaMemcpyHostToDevice, cs));
+    IEF_CUDA(cudaMemcpyAsync(m->host_in[buf][1].p, static_cast<const uint8_t*>(ev_host) + r0 * D * es, nr * D * es,
+                             cudaMemcpyHostToDevice, cs));
+    IEF_CUDA(cudaEventRecord(m->ev_copied[buf], cs));
+    IEF_CUDA(cudaStreamWaitEvent(st, m->ev_copied[buf], 0));
     float* o[7];
     for (int i = 0; i < 7; ++i) o[i] = m->host_out[i].as<float>();
-    IEF_TRY(m->impl.forward(m->host_in[0].p, m->host_in[1].p, in_dtype, Bs, T, o[0], m->host_logits.as<float>(), o[1],
-                            o[2], o[3], o[4], o[5], o[6], scores_host ? m->host_scores.as<float>() : nullptr, st));
-    IEF_CUDA(cudaMemcpyAsync(logits_host + r0, m->host_logits.p, nr * 4, cudaMemcpyDeviceToHost, st));
-    if (scores_host) IEF_CUDA(cudaMemcpyAsync(scores_host + r0, m->host_scores.p, nr * 4, cudaMemcpyDeviceToHost, st));
+    IEF_TRY(m->impl.forward(m->host_in[buf][0].p, m->host_in[buf][1].p, in_dtype, Bs, T, o[0], ldev + r0, o[1], o[2], o[3],
+                            o[4], o[5], o[6], sdev ? sdev + r0 : nullptr, st));
+    IEF_CUDA(cudaEventRecord(m->ev_consumed[buf], st));
+    if (logits_host) IEF_CUDA(cudaMemcpyAsync(logits_host + r0, ldev + r0, nr * 4, cudaMemcpyDeviceToHost, st));
+    if (scores_host) IEF_CUDA(cudaMemcpyAsync(scores_host + r0, sdev + r0, nr * 4, cudaMemcpyDeviceToHost, st));
   }
+  return IEFVAD_OK;
+}
+
+int iefvad_model_forward_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
+                              int64_t T, float* logits_host, float* scores_host, void* stream) {
+  IEF_CHECK(logits_host, "iefvad_model_forward_host: null logits_host");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  IEF_TRY(forward_from_host(m, img_host, ev_host, in_dtype, B, T, logits_host, scores_host, nullptr, nullptr, st));
   IEF_CUDA(cudaStreamSynchronize(st));
+  return IEFVAD_OK;
+}
+
+int iefvad_model_forward_host_to_device(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype,
+                                        int64_t B, int64_t T, float* logits, float* scores, void* stream) {
+  IEF_CHECK(logits, "iefvad_model_forward_host_to_device: null logits");
+  return forward_from_host(m, img_host, ev_host, in_dtype, B, T, nullptr, nullptr, logits, scores,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_model_set_host_part_rows(iefvad_model* m, int64_t rows) {
+  IEF_CHECK(m && rows >= 1, "iefvad_model_set_host_part_rows: need a model and rows >= 1");
+  m->host_part_rows = rows;
   return IEFVAD_OK;
 }
 

@@ -140,15 +140,18 @@ class Evaluator:
         """Pinned host staging for the end-to-end path (H2D inside every step)."""
         self._pinned = (img_chunks if img_chunks.is_pinned() else img_chunks.pin_memory(),
                         ev_chunks if ev_chunks.is_pinned() else ev_chunks.pin_memory())
-        self._img = torch.empty(self._pinned[0].shape, dtype=self._pinned[0].dtype, device=self.device)
-        self._ev = torch.empty_like(self._img)
+        self._img = self._ev = None
 
     # ------------------------------------------------------------------ one evaluation pass
-    def local_scores(self) -> torch.Tensor:
-        """Forward over all my chunks -> compacted sigmoid scores of my valid rows (device, fp32)."""
+    def local_scores(self, host_inputs: bool = False) -> torch.Tensor:
+        """Forward over all my chunks -> compacted sigmoid scores of my valid rows (device, fp32).  With host_inputs the
+        pinned host features go through the library's pipelined host-input forward (copy overlapped with compute)."""
         packed = torch.empty(max(self.max_count, 1), dtype=torch.float32, device=self.device)
         if self.local_chunks:
-            out = self.model.temporal(self._img, self._ev, with_scores=True)
+            if host_inputs:
+                out = self.model.temporal.scores_from_host(self._pinned[0], self._pinned[1], self.device)
+            else:
+                out = self.model.temporal(self._img, self._ev, with_scores=True)
             _segment_copy(out["scores"], self._src_off, packed, self._dst_off, self._len)
         return packed
 
@@ -192,10 +195,7 @@ class Evaluator:
     def step(self, host_inputs: bool = False, with_metrics: bool = True, sync: bool = True) -> Dict[str, object]:
         """One evaluation pass.  With sync=False nothing waits for the device: the returned dict holds the device
         score vector and, under "pending", the pinned metrics table to hand to `finish()` later."""
-        if host_inputs:
-            self._img.copy_(self._pinned[0], non_blocking=True)
-            self._ev.copy_(self._pinned[1], non_blocking=True)
-        scores = self.gather(self.local_scores())
+        scores = self.gather(self.local_scores(host_inputs))
         res: Dict[str, object] = {}
         if with_metrics:
             pending = self.metrics_async(scores)

@@ -157,6 +157,35 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         return out
 
 
+    def scores_from_host(self, img_host: torch.Tensor, ev_host: torch.Tensor, device) -> Dict[str, torch.Tensor]:
+        """Inference from HOST (ideally pinned) [B, T, D] inputs: the library pipelines the host->device copy with the
+        forward (iefvad_model_forward_host_to_device) and returns device `logits` [B, T, 1] and `scores` [B, T];
+        nothing waits for the device.  The host tensors must stay alive and unchanged until the stream has run."""
+        if img_host.is_cuda or ev_host.is_cuda:
+            raise RuntimeError("scores_from_host takes host tensors; use forward() for device tensors")
+        if img_host.dim() != 3 or img_host.shape != ev_host.shape or img_host.shape[-1] != self.embed_dim:
+            raise RuntimeError(f"expected two [B, T, {self.embed_dim}] host tensors")
+        codes = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+        if img_host.dtype not in codes or ev_host.dtype != img_host.dtype:
+            raise RuntimeError("host inputs must share one of the dtypes float32 / float16 / bfloat16")
+        img, ev = img_host.contiguous(), ev_host.contiguous()
+        device = torch.device(device)
+        plan = _lib.PLANS.get(str(self.precision))
+        if plan is None:
+            raise ValueError(f"unknown precision plan {self.precision!r}; choose from {sorted(_lib.PLANS)}")
+        B, T, _ = img.shape
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            h = self._native(device)
+            self._sync_params(h, device, stream)
+            _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
+            logits = torch.empty((B, T, 1), dtype=torch.float32, device=device)
+            scores = torch.empty((B, T), dtype=torch.float32, device=device)
+            _lib.check(_lib.lib.iefvad_model_forward_host_to_device(
+                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], B, T, logits.data_ptr(), scores.data_ptr(), stream))
+        return {"logits": logits, "scores": scores, "_keepalive": (img, ev)}
+
+
 class MMFMIL(nn.Module):
     """model/imf_vad.py:5-44: holds the bookkeeping attributes and forwards to `self.temporal`."""
 

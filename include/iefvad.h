@@ -85,6 +85,16 @@ int iefvad_model_forward(iefvad_model* m, const void* img, const void* ev, int i
 int iefvad_model_forward_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
                               int64_t T, float* logits_host, float* scores_host, void* stream);
 
+/* The same host-input path with DEVICE results and no host synchronisation: logits [B*T] (and scores, optional)
+ * are written to device memory on `stream` - the form the batched evaluator uses (scores feed the on-device
+ * compaction and AUC).  Both host-input calls pipeline the transfer: the batch is cut into parts of whole batch
+ * elements whose sizes grow geometrically (x 1.4) from `host_part_rows` / 4 rows (default 32768 / 4), and part
+ * p+1 is copied on an internal copy stream while part p computes, so only the small first part's copy is exposed.  The host buffers must stay valid and unchanged
+ * until `stream` has finished the call. */
+int iefvad_model_forward_host_to_device(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype,
+                                        int64_t B, int64_t T, float* logits, float* scores, void* stream);
+int iefvad_model_set_host_part_rows(iefvad_model* m, int64_t rows);
+
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone operators (device pointers) - the same kernels the forward uses, exposed for parity tests
  * ---------------------------------------------------------------------------------------------- */

@@ -177,3 +177,33 @@ def test_load_state_dict_refreshes_device_weights(pkg, full):
         m.load_state_dict(sd)
         back = m(img[None].cuda(), ev[None].cuda(), None, None, None)["logits"]
         assert torch.equal(back, base)
+
+
+def test_host_input_pipeline_equals_device_forward(pkg, full):
+    """iefvad_model_forward_host_to_device / _forward_host (copy of part p+1 overlapped with the forward of part p,
+    ping-pong input buffers) give bit-identical scores to the device-input forward, for part sizes that do and do
+    not divide the batch, and across repeated calls (buffer reuse between calls)."""
+    import ctypes as C
+    from iefvad_b200 import _lib
+    _, synth = pkg
+    m, _ = full["full_default"]
+    m.temporal.precision = "H"
+    img, ev = synth.make_video(11, 256 * 7 + 40)
+    ci, ce = synth.chunk_video(img), synth.chunk_video(ev)            # [8, 256, 768] fp16 on the host
+    pi, pe = ci.pin_memory(), ce.pin_memory()
+    with torch.no_grad():
+        ref = m.temporal(ci.cuda(), ce.cuda(), with_scores=True)
+        for part_rows in (256, 768, 1024, 4096):
+            _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, part_rows))
+            for _ in range(2):
+                out = m.temporal.scores_from_host(pi, pe, torch.device("cuda", 0))
+                torch.cuda.synchronize()
+                assert torch.equal(out["scores"], ref["scores"]) and torch.equal(out["logits"], ref["logits"])
+        # the synchronous host-output entry point
+        lg = torch.empty(ci.shape[0] * ci.shape[1], dtype=torch.float32).pin_memory()
+        sc = torch.empty_like(lg).pin_memory()
+        _lib.check(_lib.lib.iefvad_model_forward_host(m.temporal._handle, pi.data_ptr(), pe.data_ptr(), _lib.F16,
+                                                      ci.shape[0], ci.shape[1], lg.data_ptr(), sc.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream))
+        assert torch.equal(sc, ref["scores"].reshape(-1).cpu()) and torch.equal(lg, ref["logits"].reshape(-1).cpu())
+        _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, 32768))
