@@ -35,7 +35,7 @@ import torch  # noqa: E402
 FLOPS_PER_FRAME_T256 = 47_187_456 + 12_288 * 256          # SURVEY.md 8d, algorithmic
 # operand types of the tensor-core contractions per precision plan (accumulation, residual stream, LayerNorm, softmax
 # statistics, fusion and classifier are fp32 in every plan)
-DTYPES = {"H": "bf16 (encoder, heads: 3-term split) + fp16 (refinement) operands, fp32 accumulate",
+DTYPES = {"H": "fp16 operands (encoder, refinement) + bf16 3-term split (heads), fp32 accumulate",
           "B": "bf16 operands (heads + refinement: 3-term split), fp32 accumulate",
           "A": "bf16 operands (heads: 3-term split), fp32 accumulate", "bf16": "bf16 operands, fp32 accumulate",
           "split": "bf16 operands, 3-term split everywhere, fp32 accumulate", "fp32": "f32"}
@@ -203,13 +203,115 @@ def cpu_port_run(workload, sample_videos: int, steps: int, warmup: int, synth):
     return frames / dt, dt * 1e3, cores, f"first {len(lengths)} videos of the workload ({frames} frames), per-video loop"
 
 
+def direct_workload(args, desc, synth):
+    """Configs 1 / 4 / 5: the reference-shaped module called directly on one [B, T, 768] batch (no chunking loop).
+    Inputs are smaller than L2, so L2 is flushed (256 MB write) before every timed iteration and each iteration has
+    its own CUDA-event pair."""
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    from iefvad_b200 import _lib
+    from iefvad_b200.imf_vad import MMFMIL
+    from iefvad_b200.loss import CLAS2
+    model = synth.build_model(MMFMIL, seed=0).to(dev).eval()
+    if args.plan:
+        model.temporal.precision = args.plan
+    lengths = labels = None
+    if args.workload == "c1":
+        img, ev = (t[None] for t in synth.make_video(0, 256))
+    elif args.workload == "c5":
+        img, ev = (t[None] for t in synth.make_video(30, 16384))
+    else:
+        img, ev, lengths, labels = synth.make_c4_batch()
+        lengths, labels = lengths.to(dev), labels.to(dev)
+    B, T, D = img.shape
+    frames = B * T
+    d_img, d_ev = img.to(dev), ev.to(dev)
+    p_img, p_ev = img.pin_memory(), ev.pin_memory()
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    def run(host: bool):
+        if host:
+            out = model.temporal.scores_from_host(p_img, p_ev, dev)
+        else:
+            out = model.temporal(d_img, d_ev, with_scores=True)
+        if lengths is not None:
+            return CLAS2(out["logits"], labels, lengths, dev)
+        return out["scores"]
+
+    def timed(host: bool, steps: int):
+        tot = 0.0
+        res = None
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = run(host)
+            if host:
+                res = res.to("cpu", non_blocking=True) if res.numel() == 1 else res[:, :1].to("cpu", non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / steps, res
+
+    with torch.no_grad():
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
+        for _ in range(max(3, args.warmup)):
+            run(False)
+        l0 = _lib.lib.iefvad_launch_count()
+        sampler.recording = True
+        ms_dev, res = timed(False, args.steps)
+        sampler.recording = False
+        launches = _lib.lib.iefvad_launch_count() - l0
+        clocks = sampler.stop()
+        for _ in range(2):
+            run(True)
+        ms_e2e, _ = timed(True, max(2, args.steps // 2))
+    flops = frames * (47_187_456 + 12_288 * T)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import torch_port
+        torch.set_num_threads(os.cpu_count() or 1)
+        P = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        with torch.no_grad():
+            torch_port.forward(P, img[:1, :min(T, 2048)], ev[:1, :min(T, 2048)])
+            t0 = time.perf_counter()
+            sample_B = min(B, 8)
+            sample_T = T if T <= 4096 else 4096
+            torch_port.forward(P, img[:sample_B, :sample_T], ev[:sample_B, :sample_T])
+            dt = time.perf_counter() - t0
+        cpu = {"value": round(sample_B * sample_T / dt, 1), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle torch-CPU port, [{sample_B}, {sample_T}, {D}] slice of the batch"
+                         + (" (attention span truncated to 4096: the full T=16384 call takes ~25 s / 12 GB)" if T > 4096 else "")}
+    line = {"metric": "fused frames/sec (IEF-VAD inference)", "value": round(frames / (ms_dev * 1e-3), 1),
+            "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": round(ms_dev, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPES.get(str(model.temporal.precision), "bf16"), "data": "synthetic",
+            "config": {"workload": desc, "batch": B, "T": T, "precision_plan": model.temporal.precision,
+                       "l2": "L2 flushed (256 MB write) before every timed iteration"},
+            "e2e": {"value": round(frames / (ms_e2e * 1e-3), 1), "unit": "frames/s", "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": int(2 * img.numel() * img.element_size()), "d2h_bytes_per_step": 4 * (1 if lengths is not None else B)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "forward_tflops_algorithmic": round(flops / (ms_dev * 1e-3) / 1e12, 2),
+            "roofline": {"bound": "tensor", "kernel": "whole forward (tcgen05 GEMMs + attention)",
+                         "achieved": round(flops / (ms_dev * 1e-3) / 1e12, 2), "peak": float(peaks()["bf16_tflops_sustained"]),
+                         "unit": "TFLOP/s", "frac": round(flops / (ms_dev * 1e-3) / 1e12 / float(peaks()["bf16_tflops_sustained"]), 4),
+                         "traffic": None, "note": "algorithmic FLOPs of the forward (47 187 456 + 12 288 T per frame) / device time"},
+            "result": float(res.reshape(-1)[0]) if res is not None else None,
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ucf", choices=["ucf", "xd", "c1"])
+    ap.add_argument("--workload", default="ucf", choices=["ucf", "xd", "c1", "c4", "c5"],
+                    help="ucf = BASELINE configs[1] (default, the headline); xd = configs[2]; c1 / c4 / c5 = direct "
+                         "module calls of configs[0] (B=1,T=256), [3] (B=64,T=256 + CLAS2), [4] (B=1,T=16384)")
     ap.add_argument("--plan", default=None, help="precision plan override: H (default), B, A, bf16, split, fp32")
     ap.add_argument("--cpu-sample", type=int, default=24, help="videos in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -222,7 +324,11 @@ def main():
 
     workload_names = {"ucf": "UCF-Crime test-split shape: 290 synthetic videos, T_v<=4096, 768-d fp16 image+event, "
                              "chunked to 256 rows (data/tools.py:100-114)",
-                      "xd": "XD-Violence test-split shape: 800 synthetic videos", "c1": "B=1, T=256"}
+                      "xd": "XD-Violence test-split shape: 800 synthetic videos", "c1": "B=1, T=256",
+                      "c4": "train-step shape: forward + CLAS2 top-k loss, B=64 x T=256 clips (train/ucf_train.py:44-73)",
+                      "c5": "long-sequence stress: one video, T=16384, direct call (attention over all 16384 keys)"}
+    if args.workload in ("c1", "c4", "c5") and args.impl != "reference":
+        return direct_workload(args, workload_names[args.workload], synth)
 
     if args.impl == "reference":
         if rank != 0:

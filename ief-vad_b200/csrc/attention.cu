@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(192, AttnCfg<DH, DHP, KB>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H,
                const float* __restrict__ attn_mask /* [T,T] additive or null */,
-               const uint8_t* __restrict__ key_pad /* [B,T] 1 = ignore, or null */) {
+               const uint8_t* __restrict__ key_pad /* [B,T] 1 = ignore, or null */, int fp16, int out_fp16) {
   using Cfg = AttnCfg<DH, DHP, KB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -114,8 +114,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(QB, KB);
-      constexpr uint32_t idesc_o = make_idesc_bf16(QB, DH);
+      const uint32_t idesc_s = fp16 ? make_idesc_f16(QB, KB) : make_idesc_bf16(QB, KB);
+      const uint32_t idesc_o = fp16 ? make_idesc_f16(QB, DH) : make_idesc_bf16(QB, DH);
       const uint32_t sq = smem_u32(smem);
       auto issue_s = [&](int j) {
         const int s = j & 1;
@@ -249,10 +249,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
-          u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-          u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-          u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-          u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+          u.x = pack_16x2(v[g * 8 + 0], v[g * 8 + 1], fp16);
+          u.y = pack_16x2(v[g * 8 + 2], v[g * 8 + 3], fp16);
+          u.z = pack_16x2(v[g * 8 + 4], v[g * 8 + 5], fp16);
+          u.w = pack_16x2(v[g * 8 + 6], v[g * 8 + 7], fp16);
           const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
           *reinterpret_cast<uint4*>(ptile + chunk * 16) = u;
         }
@@ -280,10 +280,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
       for (int d = 0; d < DH; d += 8) {
         uint4 u;
-        u.x = pack_bf16x2(o_acc[d + 0] * inv, o_acc[d + 1] * inv);
-        u.y = pack_bf16x2(o_acc[d + 2] * inv, o_acc[d + 3] * inv);
-        u.z = pack_bf16x2(o_acc[d + 4] * inv, o_acc[d + 5] * inv);
-        u.w = pack_bf16x2(o_acc[d + 6] * inv, o_acc[d + 7] * inv);
+        u.x = pack_16x2(o_acc[d + 0] * inv, o_acc[d + 1] * inv, out_fp16);
+        u.y = pack_16x2(o_acc[d + 2] * inv, o_acc[d + 3] * inv, out_fp16);
+        u.z = pack_16x2(o_acc[d + 4] * inv, o_acc[d + 5] * inv, out_fp16);
+        u.w = pack_16x2(o_acc[d + 6] * inv, o_acc[d + 7] * inv, out_fp16);
         *reinterpret_cast<uint4*>(dst + d) = u;
       }
     }
@@ -313,7 +313,7 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
   IEF_TRY(make_tmap_3d(&tv, a.vt, a.T, DH, BH, uint64_t(a.Tpad) * 2, uint64_t(DH) * a.Tpad * 2, 64, DH, 1));
   dim3 grid((a.T + QB - 1) / QB, a.H, a.B);
   attn_tc_kernel<DH, DHP, KB><<<grid, 192, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, a.attn_mask,
-                                                                  a.key_pad);
+                                                                  a.key_pad, a.fp16, a.out_fp16);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

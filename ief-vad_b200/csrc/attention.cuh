@@ -12,6 +12,8 @@ struct AttnTcArgs {
   int B = 0, T = 0, H = 0, dh = 0, dhp = 0, Tpad = 0;
   const float* attn_mask = nullptr;    // optional additive [T, T]
   const uint8_t* key_pad = nullptr;    // optional [B, T], non-zero = ignore key
+  int fp16 = 0;                        // q / k / vt hold fp16 and P is rounded to fp16 (11-bit mantissa), else bf16
+  int out_fp16 = 0;                    // `out` receives fp16 instead of bf16
   int key_block = 0;                   // 0 = heuristic (64 keys per block up to T = 2048, else 128), or 64 / 128
 };
 

@@ -96,7 +96,7 @@ int iefvad_model_set_param(iefvad_model* m, const char* key, const float* data, 
 
 int iefvad_model_set_plan(iefvad_model* m, int plan) {
   IEF_CHECK(m, "null model");
-  IEF_CHECK(plan == IEFVAD_PLAN_FP32 || (plan >= 0 && plan <= 15), "unknown precision plan %d", plan);
+  IEF_CHECK(plan == IEFVAD_PLAN_FP32 || (plan >= 0 && plan <= 31), "unknown precision plan %d", plan);
   m->impl.plan = plan;
   return IEFVAD_OK;
 }

@@ -50,6 +50,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// two floats -> packed 16-bit pair in either operand format (fp16 when `f16` != 0, else bf16); .x = a in the low half
+__device__ __forceinline__ uint32_t pack_16x2(float a, float b, int f16) {
+  if (f16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return pack_bf16x2(a, b);
+}
+
 // hi = bf16(x), lo = bf16(x - hi): x ~= hi + lo to ~16 mantissa bits
 __device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
   hi = __float2bfloat16_rn(x);

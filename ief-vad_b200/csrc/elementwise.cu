@@ -51,7 +51,7 @@ __device__ __forceinline__ void load8<bf16>(const bf16* p, float* v) {
 template <typename Tin>
 __global__ void __launch_bounds__(kThreads)
 ingest_kernel(const Tin* __restrict__ in, long long n8, float* __restrict__ out_f32, bf16* __restrict__ out_hi,
-              bf16* __restrict__ out_lo) {
+              bf16* __restrict__ out_lo, int hi_fp16) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float v[8];
     load8<Tin>(in + i * 8, v);
@@ -63,6 +63,11 @@ ingest_kernel(const Tin* __restrict__ in, long long n8, float* __restrict__ out_
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+      if (hi_fp16) {                          // fp16 operand copy (exact for fp16 inputs), no lo part
+        hi[q] = pack_16x2(v[2 * q], v[2 * q + 1], 1);
+        lo[q] = 0u;
+        continue;
+      }
       const bf16 ah = __float2bfloat16_rn(v[2 * q]), bh = __float2bfloat16_rn(v[2 * q + 1]);
       hi[q] = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
       lo[q] = pack_bf16x2(v[2 * q] - __bfloat162float(ah), v[2 * q + 1] - __bfloat162float(bh));
@@ -77,7 +82,7 @@ template <int NV>   // D = 128 * NV
 __global__ void __launch_bounds__(kThreads)
 layernorm_kernel(const float* __restrict__ x, long long M, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, const float* __restrict__ b2, float eps, float* __restrict__ out_f32,
-                 bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                 bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int hi_fp16) {
   constexpr int D = 128 * NV;
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -119,7 +124,12 @@ layernorm_kernel(const float* __restrict__ x, long long M, const float* __restri
     for (int i = 0; i < NV; ++i) {
       const long long off = row * D + (lane + 32 * i) * 4;
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      if (out_hi) {
+      if (out_hi && hi_fp16) {
+        uint2 u;
+        u.x = pack_16x2(v[4 * i], v[4 * i + 1], 1);
+        u.y = pack_16x2(v[4 * i + 2], v[4 * i + 3], 1);
+        *reinterpret_cast<uint2*>(out_hi + off) = u;
+      } else if (out_hi) {
         bf16 h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) split_bf16(v[4 * i + e], h[e], l[e]);
@@ -205,20 +215,20 @@ classifier_kernel(const float* __restrict__ x, long long M, int D, const float* 
 }  // namespace
 
 int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms,
-           cudaStream_t stream) {
+           cudaStream_t stream, int hi_fp16) {
   IEF_CHECK(n % 8 == 0, "ingest: element count %lld must be a multiple of 8", n);
   if (n == 0) return IEFVAD_OK;
   const long long n8 = n / 8;
   const int grid = grid_for(n8, num_sms);
   switch (dtype) {
     case IEFVAD_DT_F32:
-      ingest_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(in), n8, out_f32, out_hi, out_lo);
+      ingest_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(in), n8, out_f32, out_hi, out_lo, hi_fp16);
       break;
     case IEFVAD_DT_F16:
-      ingest_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half*>(in), n8, out_f32, out_hi, out_lo);
+      ingest_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half*>(in), n8, out_f32, out_hi, out_lo, hi_fp16);
       break;
     case IEFVAD_DT_BF16:
-      ingest_kernel<bf16><<<grid, kThreads, 0, stream>>>(static_cast<const bf16*>(in), n8, out_f32, out_hi, out_lo);
+      ingest_kernel<bf16><<<grid, kThreads, 0, stream>>>(static_cast<const bf16*>(in), n8, out_f32, out_hi, out_lo, hi_fp16);
       break;
     default:
       set_error("ingest: unsupported dtype code %d (0 = f32, 1 = f16, 2 = bf16)", dtype);
@@ -230,14 +240,14 @@ int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi,
 }
 
 int layernorm(const float* x, long long M, int D, const float* w1, const float* b1, const float* w2, const float* b2,
-              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream) {
+              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream, int hi_fp16) {
   IEF_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: D=%d must be a multiple of 128 in [128, 1024]", D);
   IEF_CHECK(w1 && b1 && (w2 == nullptr) == (b2 == nullptr), "layernorm: bad affine pointers");
   if (M == 0) return IEFVAD_OK;
   const int grid = grid_for(M * 32, num_sms);
 #define IEF_LN(NV)                                                                                              \
   case NV:                                                                                                      \
-    layernorm_kernel<NV><<<grid, kThreads, 0, stream>>>(x, M, w1, b1, w2, b2, eps, out_f32, out_hi, out_lo);  \
+    layernorm_kernel<NV><<<grid, kThreads, 0, stream>>>(x, M, w1, b1, w2, b2, eps, out_f32, out_hi, out_lo, hi_fp16);  \
     break;
   switch (D / 128) {
     IEF_LN(1) IEF_LN(2) IEF_LN(3) IEF_LN(4) IEF_LN(5) IEF_LN(6) IEF_LN(7) IEF_LN(8)

@@ -7,11 +7,12 @@ enum : int { IEFVAD_DT_F32 = 0, IEFVAD_DT_F16 = 1, IEFVAD_DT_BF16 = 2 };
 
 // in (f32 / f16 / bf16, n elements, n % 8 == 0) -> optional fp32 copy, optional bf16 hi, optional bf16 lo
 int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms,
-           cudaStream_t stream);
+           cudaStream_t stream, int hi_fp16 = 0 /* out_hi receives fp16 instead of bf16 (no lo) */);
 
 // out = LN(x; w1, b1) or LN(LN(x; w1, b1); w2, b2) when w2 != null.  x [M, D] fp32.
 int layernorm(const float* x, long long M, int D, const float* w1, const float* b1, const float* w2, const float* b2,
-              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream);
+              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream,
+              int hi_fp16 = 0 /* out_hi receives fp16 instead of bf16 (no lo) */);
 
 // model/imf_vad.py:130-144.  n elements; fused / fused_hi / fused_lo optional.
 int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long n, float factor,

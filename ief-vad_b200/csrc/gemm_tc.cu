@@ -301,7 +301,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
           if (row < M) {
             bf16* dst = ep.vt + ((b * ep.H + h) * ep.dh + d0) * (long long)ep.Tpad + t;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[(long long)j * ep.Tpad] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j) {
+              if (ep.hi_fp16) reinterpret_cast<__half*>(dst)[(long long)j * ep.Tpad] = __float2half_rn(v[j]);
+              else dst[(long long)j * ep.Tpad] = __float2bfloat16_rn(v[j]);
+            }
           }
           return;
         }
@@ -309,10 +312,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
         uint4 u[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          u[g].x = pack_bf16x2(v[g * 8 + 0] * s, v[g * 8 + 1] * s);
-          u[g].y = pack_bf16x2(v[g * 8 + 2] * s, v[g * 8 + 3] * s);
-          u[g].z = pack_bf16x2(v[g * 8 + 4] * s, v[g * 8 + 5] * s);
-          u[g].w = pack_bf16x2(v[g * 8 + 6] * s, v[g * 8 + 7] * s);
+          u[g].x = pack_16x2(v[g * 8 + 0] * s, v[g * 8 + 1] * s, ep.hi_fp16);
+          u[g].y = pack_16x2(v[g * 8 + 2] * s, v[g * 8 + 3] * s, ep.hi_fp16);
+          u[g].z = pack_16x2(v[g * 8 + 4] * s, v[g * 8 + 5] * s, ep.hi_fp16);
+          u[g].w = pack_16x2(v[g * 8 + 6] * s, v[g * 8 + 7] * s, ep.hi_fp16);
         }
         if (!ep.qk_tma) {
           if (row < M) {

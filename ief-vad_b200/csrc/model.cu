@@ -112,11 +112,11 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
       Linear& op = out_proj[m][i];
       ip.out = 3 * D; ip.in = D; op.out = D; op.in = D;
       snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.in_proj_weight", mods[m], i);
-      wants.push_back({buf, 3LL * D * D, true, &ip.w, &ip.w_hi, &ip.w_lo});
+      wants.push_back({buf, 3LL * D * D, true, &ip.w, &ip.w_hi, &ip.w_lo, &ip.w_h16});
       snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.in_proj_bias", mods[m], i);
       wants.push_back({buf, 3LL * D, false, &ip.b, nullptr, nullptr});
       snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.out_proj.weight", mods[m], i);
-      wants.push_back({buf, 1LL * D * D, true, &op.w, &op.w_hi, &op.w_lo});
+      wants.push_back({buf, 1LL * D * D, true, &op.w, &op.w_hi, &op.w_lo, &op.w_h16});
       snprintf(buf, sizeof(buf), "temporal.%s_attn_layers.%d.out_proj.bias", mods[m], i);
       wants.push_back({buf, D, false, &op.b, nullptr, nullptr});
       snprintf(buf, sizeof(buf), "temporal.%s_norms.%d.weight", mods[m], i);
@@ -272,8 +272,10 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     const long long row0 = b0 * T;
     for (int m = 0; m < 2; ++m) {
       const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + size_t(row0) * D * in_esize;
+      const int e16 = (!fp32_plan && (plan & PLAN_FP16_ATTENTION)) ? 1 : 0;      // encoder operands in fp16
+      const bool esp = !fp32_plan && !e16 && (plan & PLAN_SPLIT_ENCODER);
       IEF_PROF(KC_INGEST, double(M) * D * (in_esize + 4 + 2), ingest(in, in_dtype, M * D, x32.as<float>(), fp32_plan ? nullptr : a_hi.as<bf16>(),
-                     (!fp32_plan && (plan & PLAN_SPLIT_ENCODER)) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+                     esp ? a_lo.as<bf16>() : nullptr, num_sms, stream, (e16 && L > 0) ? 1 : 0));
       for (int i = 0; i < L; ++i) {                                   // model/imf_vad.py:114-116 / :120-122
         const Linear& ip = in_proj[m][i];
         const Linear& op = out_proj[m][i];
@@ -289,28 +291,32 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
                             last ? whiten_b[m] : nullptr, 1e-5f, x32.as<float>(), nullptr, nullptr, num_sms, stream));
         } else {
-          const bool sp = (plan & PLAN_SPLIT_ENCODER) != 0;
+          const bool sp = esp;
+          const int a16 = e16;
           EpiParams e1;
+          e1.hi_fp16 = a16;
           e1.mode = EPI_QKV; e1.bias = ip.b; e1.q = qb.as<bf16>(); e1.k = kb.as<bf16>(); e1.vt = vtb.as<bf16>();
           e1.T = int(T); e1.H = H; e1.dh = dh; e1.dhp = dhp; e1.Tpad = Tpad; e1.D = D; e1.qscale = qscale;
           GemmTcArgs g1;
-          g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = ip.w_hi; g1.W_lo = ip.w_lo;
-          g1.M = int(M); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1;
+          g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = a16 ? ip.w_h16 : ip.w_hi; g1.W_lo = ip.w_lo;
+          g1.M = int(M); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1; g1.fp16 = a16;
           IEF_PROF(KC_GEMM_QKV, 6.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
           AttnTcArgs at;
           at.q = qb.as<bf16>(); at.k = kb.as<bf16>(); at.vt = vtb.as<bf16>(); at.out = h_hi.as<bf16>(); at.ldo = D;
           at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
+          at.fp16 = a16; at.out_fp16 = a16;
           IEF_PROF(KC_ATTN_TC, 4.0 * M * T * D, attn_tc(at, stream));
           EpiParams e2;
           e2.bias = op.b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.out_f32 = y32.as<float>(); e2.ld_f32 = D;
           GemmTcArgs g2;
-          g2.A_hi = h_hi.as<bf16>(); g2.W_hi = op.w_hi; g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
+          g2.A_hi = h_hi.as<bf16>(); g2.W_hi = a16 ? op.w_h16 : op.w_hi; g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
+          g2.fp16 = a16;
           IEF_PROF(KC_GEMM_OUT, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
           // LN_i (+ whitening LN after the last layer, :117/:123); bf16 hi(/lo) feed the next GEMM
           const bool need_lo = last ? (plan & PLAN_SPLIT_HEADS) != 0 : sp;
           IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
                             last ? whiten_b[m] : nullptr, 1e-5f, last ? nullptr : x32.as<float>(), a_hi.as<bf16>(),
-                            need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+                            need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream, (a16 && !last) ? 1 : 0));
         }
       }
       if (L == 0) {

@@ -16,7 +16,11 @@ namespace iefvad {
 // 3-term split (A_hi.W_hi + A_hi.W_lo + A_lo.W_hi)
 // PLAN_FP16_REFINE: the refinement Linears take fp16 (E5M10) operands in a single MMA pass instead of the 3-term bf16
 // split - the same 8.5e-5 score error at a third of the MMA work
-enum : int { PLAN_FP32 = -1, PLAN_SPLIT_ENCODER = 1, PLAN_SPLIT_HEADS = 2, PLAN_SPLIT_REFINE = 4, PLAN_FP16_REFINE = 8 };
+// PLAN_FP16_ATTENTION: the encoder (in-projection, q / k / v / P of the attention core, out-projection) uses fp16
+// operands - fp16 inputs are then exact, and the attention core is where bf16's mantissa dominates the error once the
+// heads / refinement are taken care of (zero-padded clips: 1.4e-3 with bf16, 1.7e-4 with fp16)
+enum : int { PLAN_FP32 = -1, PLAN_SPLIT_ENCODER = 1, PLAN_SPLIT_HEADS = 2, PLAN_SPLIT_REFINE = 4, PLAN_FP16_REFINE = 8,
+             PLAN_FP16_ATTENTION = 16 };
 
 struct DevBuf {
   void* p = nullptr;
@@ -47,7 +51,7 @@ struct ParamSlot {
 struct Model {
   int D = 0, H = 0, L = 0, R = 0, dh = 0, dhp = 0;
   float lambda_ref = 0.5f, factor = 1.f, eps = 1e-8f;
-  int plan = PLAN_SPLIT_HEADS | PLAN_FP16_REFINE;
+  int plan = PLAN_SPLIT_HEADS | PLAN_FP16_REFINE | PLAN_FP16_ATTENTION;
   long long max_rows = 262144;   // rows per internal slab (whole batch elements); ~18 KB of workspace per row
   int num_sms = 148;
   int device = 0;

@@ -105,3 +105,20 @@ def make_gt(lengths, classes) -> np.ndarray:
             g[4 * int(T):9 * int(T)] = 1.0
         parts.append(g)
     return np.concatenate(parts) if parts else np.zeros(0)
+
+
+def make_c4_batch(B: int = 64, T: int = 256, seed: int = 4, num_class: int = 14):
+    """Config 4 (train/ucf_train.py:44-73 shape): B zero-padded clips of T rows, lengths ~ U{16..T}, first half
+    normal.  -> (img [B,T,D] fp16, ev [B,T,D] fp16, lengths int64 [B], labels fp32 [B, num_class])."""
+    rng = np.random.default_rng(seed)
+    lengths = rng.integers(16, T + 1, B)
+    clips = [make_video(100 + i, T) for i in range(B)]
+    img = torch.stack([c[0] for c in clips])
+    ev = torch.stack([c[1] for c in clips])
+    for i in range(B):                                        # process_feat zero-pads short clips (data/tools.py:89-97)
+        img[i, int(lengths[i]):] = 0
+        ev[i, int(lengths[i]):] = 0
+    labels = torch.zeros(B, num_class)
+    labels[: B // 2, 0] = 1.0
+    labels[B // 2:, 1 + (torch.arange(B - B // 2) % (num_class - 1))] = 1.0
+    return img, ev, torch.from_numpy(lengths.astype(np.int64)), labels

@@ -43,7 +43,9 @@ extern "C" {
 #define IEFVAD_PLAN_FP16_REFINE 8 /* refinement Linears: fp16 (E5M10) operands, one MMA pass, fp32 accumulate */
 #define IEFVAD_PLAN_A (IEFVAD_PLAN_SPLIT_HEADS)
 #define IEFVAD_PLAN_B (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_SPLIT_REFINE) /* bf16 operands everywhere */
-#define IEFVAD_PLAN_H (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_FP16_REFINE)  /* default: same error as B, 1/3 of its refinement MMAs */
+#define IEFVAD_PLAN_FP16_ATTENTION 16 /* encoder (QKV in-projection, attention core, out-projection): fp16 operands */
+#define IEFVAD_PLAN_H (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_FP16_REFINE | IEFVAD_PLAN_FP16_ATTENTION)
+/* ^ default: fp16 (11-bit mantissa, same tcgen05 kind::f16 rate) where bf16's 8-bit mantissa limits accuracy */
 
 int iefvad_abi_version(void);
 const char* iefvad_last_error(void);

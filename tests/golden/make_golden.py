@@ -122,6 +122,34 @@ def full_models():
         with torch.no_grad():
             out = model(img1k[None], ev1k[None], None, None, None)
         arrays["t1000:logits"] = out["logits"].numpy().reshape(-1)
+        # C4 (ucf_train.py shape): B=64 clips of T=256 (train/ucf_train.py:44-48 feeds pooled / padded 256-row clips),
+        # eval-mode forward + the reference's CLAS2 (train/loss.py:18-30) with lengths ~ U{16..256}, half normal labels
+        rng = np.random.default_rng(4)
+        B4 = 64
+        lengths = rng.integers(16, 257, B4)
+        clips = [synth.make_video(100 + i, 256) for i in range(B4)]
+        img4 = torch.stack([c[0] for c in clips])
+        ev4 = torch.stack([c[1] for c in clips])
+        for i in range(B4):                                    # process_feat zero-pads short clips (data/tools.py:89-97)
+            img4[i, int(lengths[i]):] = 0
+            ev4[i, int(lengths[i]):] = 0
+        labels = torch.zeros(B4, 14)
+        labels[: B4 // 2, 0] = 1.0                               # first half normal (column 0), rest abnormal
+        labels[B4 // 2:, 1 + (torch.arange(B4 // 2) % 13)] = 1.0
+        with torch.no_grad():
+            out = model(img4, ev4, None, None, torch.from_numpy(lengths))
+            loss = ref_CLAS2(out["logits"], labels, torch.from_numpy(lengths), "cpu")
+        arrays["c4:lengths"] = lengths.astype(np.int64)
+        arrays["c4:labels"] = labels.numpy()
+        arrays["c4:logits"] = out["logits"].numpy().reshape(B4, 256)
+        arrays["c4:loss"] = np.float64(float(loss))
+        # C5: one video of T=16384 fed directly (no chunking): attention over all 16384 keys
+        if os.environ.get("IEFVAD_GOLDEN_SKIP_C5") != "1":
+            img5, ev5 = synth.make_video(30, 16384)
+            with torch.no_grad():
+                out = model(img5[None], ev5[None], None, None, None)
+            arrays["c5:logits"] = out["logits"].numpy().reshape(-1)
+            arrays["c5:fused:rows"] = out["fused"].numpy()[0, rows * 64]
         save(tag + ".npz", **arrays)
 
 

@@ -207,3 +207,40 @@ def test_host_input_pipeline_equals_device_forward(pkg, full):
                                                       torch.cuda.current_stream().cuda_stream))
         assert torch.equal(sc, ref["scores"].reshape(-1).cpu()) and torch.equal(lg, ref["logits"].reshape(-1).cpu())
         _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, 32768))
+
+
+@pytest.mark.parametrize("plan", ["fp32", "H", "B"])
+def test_c4_train_shape_forward_and_clas2(pkg, full, plan):
+    """Config 4: B=64 x T=256 eval-mode forward + CLAS2 (train/ucf_train.py:60-73, train/loss.py:18-30) against the
+    reference's golden logits and loss."""
+    from iefvad_b200.loss import CLAS2
+    _, synth = pkg
+    m, z = full["full_default"]
+    m.temporal.precision = plan
+    img, ev, lengths, labels = synth.make_c4_batch()
+    with torch.no_grad():
+        out = m(img.cuda(), ev.cuda(), None, None, lengths.cuda())
+        loss = CLAS2(out["logits"], labels.cuda(), lengths.cuda(), "cuda")
+    got = out["logits"].cpu().numpy().reshape(64, 256)
+    valid = np.arange(256)[None, :] < lengths.numpy()[:, None]
+    # the frames every caller consumes (logits[i, :len], train/loss.py:24): 1e-3 in every tensor-core plan
+    assert O.score_rel_err(got[valid], z["c4:logits"][valid]) < SCORE_TOL[plan]
+    # the all-zero pad rows are the worst case for low-precision attention (their encoder output IS the attention
+    # output): the default plan keeps them within 1e-3 as well; the all-bf16 plan B measures 1.4e-3 there
+    assert O.score_rel_err(got[~valid], z["c4:logits"][~valid]) < (2e-3 if plan == "B" else SCORE_TOL[plan])
+    assert abs(float(loss) - float(z["c4:loss"])) < (1e-5 if plan == "fp32" else 2e-4)
+
+
+@pytest.mark.parametrize("plan", ["H", "B"])
+def test_c5_long_sequence_t16384(pkg, full, plan):
+    """Config 5: one video of T = 16384 fed directly (no chunking): streaming-softmax attention over 128 key blocks,
+    against the reference's golden logits (CPU fp32, 25 s / 12 GB there)."""
+    _, synth = pkg
+    m, z = full["full_default"]
+    m.temporal.precision = plan
+    img, ev = synth.make_video(30, 16384)
+    with torch.no_grad():
+        out = m(img[None].cuda(), ev[None].cuda(), None, None, None)
+    assert O.score_rel_err(out["logits"].cpu().numpy().reshape(-1), z["c5:logits"]) < SCORE_TOL[plan]
+    rows = z["c1:rows"] * 64
+    assert O.max_norm_err(out["fused"].cpu().numpy()[0, rows], z["c5:fused:rows"]) < TENSOR_TOL[plan]

@@ -90,3 +90,15 @@ def test_oracle_eval_loop_matches_reference_test(models):
     rep = np.repeat(z["scores"].astype(np.float64), 16)
     assert abs(O.roc_auc_score(gt, rep) - float(z["AUC"])) < 1e-12
     assert abs(O.average_precision_score(gt, rep) - float(z["AP"])) < 1e-12
+
+
+def test_oracle_c4_train_shape_forward_and_clas2(models):
+    """Config 4: the reference's eval-mode forward on 64 zero-padded 256-row clips + its CLAS2 loss."""
+    z = load_golden("full_default.npz")
+    P = _sd_np(models["full_default"])
+    img, ev, lengths, labels = synth.make_c4_batch()
+    assert np.array_equal(lengths.numpy(), z["c4:lengths"]) and np.array_equal(labels.numpy(), z["c4:labels"])
+    out = O.forward(P, img[:8].numpy(), ev[:8].numpy())            # batch elements are independent: 8 of 64 on the CPU
+    assert O.score_rel_err(out["logits"].reshape(8, 256), z["c4:logits"][:8]) < 2e-5
+    loss, _ = O.clas2(z["c4:logits"][..., None], labels.numpy(), lengths.numpy())
+    assert abs(float(loss) - float(z["c4:loss"])) < 1e-6
