@@ -53,6 +53,8 @@ _SIGS = {
     "iefvad_graph_convolution": (_i, [_vp] * 4 + [_i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "iefvad_distance_scan": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "iefvad_transformer": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "iefvad_process_split": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _i, _vp]),
+    "iefvad_process_feat": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _i, _vp]),
     "iefvad_bench_gemm": (_i, [_i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "iefvad_launch_count": (C.c_uint64, []),
     "iefvad_profile_enable": (_i, [_i]),

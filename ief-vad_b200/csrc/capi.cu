@@ -11,6 +11,7 @@
 #include "graph.cuh"
 #include "model.cuh"
 #include "rank.cuh"
+#include "shaping.cuh"
 
 namespace iefvad {
 const char* last_error();
@@ -405,6 +406,23 @@ int iefvad_transformer(const float* x, const float* const* params, int layers, i
   }
   return transformer(x, blocks.data(), layers, L, N, D, heads, attn_mask, key_padding_mask, plan, out, sms,
                      static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ row N2
+
+int iefvad_process_split(const void* src, int dtype, const int64_t* row_off, int64_t V, int D, int length,
+                         const int64_t* chunk_off, int64_t total_chunks, void* dst, int nan_to_num, void* stream) {
+  IEF_CHECK(dtype >= 0 && dtype <= 2, "unsupported dtype code %d", dtype);
+  return process_split(src, dtype, reinterpret_cast<const long long*>(row_off), V, D, length,
+                       reinterpret_cast<const long long*>(chunk_off), total_chunks, dst, nan_to_num,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_process_feat(const void* src, int dtype, const int64_t* row_off, int64_t V, int D, int length, float* dst,
+                        int64_t* out_len, int nan_to_num, void* stream) {
+  IEF_CHECK(dtype >= 0 && dtype <= 2, "unsupported dtype code %d", dtype);
+  return process_feat(src, dtype, reinterpret_cast<const long long*>(row_off), V, D, length, dst,
+                      reinterpret_cast<long long*>(out_len), nan_to_num, static_cast<cudaStream_t>(stream));
 }
 
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,

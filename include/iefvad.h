@@ -204,6 +204,23 @@ int iefvad_transformer(const float* x, const float* const* params, int layers, i
                        const float* attn_mask, const uint8_t* key_padding_mask, int plan, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Input shaping of the reference's data layer (data/tools.py:65-114) for a packed list of V videos:
+ * src [sum T_v, D] (element type `dtype`), row_off DEVICE int64 [V + 1] = prefix sums of T_v.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* process_split (data/tools.py:100-114): video v -> int(T_v / length) + 1 zero-padded chunks of `length` rows (one chunk
+ * when T_v < length; an extra all-zero chunk when T_v %% length == 0).  chunk_off DEVICE int64 [V + 1] = prefix sums of
+ * the chunk counts, total_chunks = chunk_off[V]; dst [total_chunks, length, D] in the input's element type.
+ * nan_to_num != 0 applies torch.nan_to_num (train/ucf_test.py:83-88). */
+int iefvad_process_split(const void* src, int dtype, const int64_t* row_off, int64_t V, int D, int length,
+                         const int64_t* chunk_off, int64_t total_chunks, void* dst, int nan_to_num, void* stream);
+
+/* process_feat (data/tools.py:89-97, is_random=False) -> dst [V, length, D] fp32, out_len DEVICE int64 [V]:
+ * T_v > length: uniform_extract (:65-73), the mean over np.linspace(0, T_v, length + 1, dtype=int32) bins; else zero-pad. */
+int iefvad_process_feat(const void* src, int dtype, const int64_t* row_off, int64_t V, int D, int length, float* dst,
+                        int64_t* out_len, int nan_to_num, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Instrumentation used by bench.py
  * ---------------------------------------------------------------------------------------------- */
 

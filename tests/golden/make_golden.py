@@ -292,8 +292,27 @@ def layer_cases():
     save("layers.npz", **arrays)
 
 
+def tools_cases():
+    """data/tools.py:65-114 run as-is: process_split / process_feat (uniform_extract, pad) on seeded ragged inputs."""
+    from data import tools as ref_tools
+    arrays = {}
+    lens = [1, 15, 100, 255, 256, 257, 300, 511, 512, 513, 1000, 4097]
+    arrays["lens"] = np.array(lens)
+    for dt_name, dt in (("f32", np.float32), ("f16", np.float16)):
+        rng = np.random.default_rng(12)
+        for t in lens:
+            feat = rng.standard_normal((t, 16)).astype(dt)
+            sp, n = ref_tools.process_split(feat, 256)
+            arrays[f"{dt_name}:{t}:split"] = np.asarray(sp)
+            arrays[f"{dt_name}:{t}:split_len"] = np.int64(n)
+            pf, m = ref_tools.process_feat(feat, 256)
+            arrays[f"{dt_name}:{t}:feat"] = np.asarray(pf)
+            arrays[f"{dt_name}:{t}:feat_len"] = np.int64(m)
+    save("tools.npz", **arrays)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["small", "full", "clas2", "eval", "sklearn", "layers"]
+    which = sys.argv[1:] or ["small", "full", "clas2", "eval", "sklearn", "layers", "tools"]
     with torch.no_grad():
         if "small" in which:
             small_models()
@@ -307,3 +326,5 @@ if __name__ == "__main__":
             sklearn_cases()
         if "layers" in which:
             layer_cases()
+        if "tools" in which:
+            tools_cases()

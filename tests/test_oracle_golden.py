@@ -119,3 +119,19 @@ def test_process_split_rules():
             assert out.shape == (S, 256, 2)
             flat = out.reshape(-1, 2)
             assert np.all(flat[:T] == f) and np.all(flat[T:] == 0)
+
+
+def test_input_shaping_restatement_matches_reference_tools():
+    """oracle process_split / process_feat / uniform_extract == data/tools.py:65-114 run as-is (tests/golden/tools.npz)."""
+    z = load_golden("tools.npz")
+    for dt_name, dt in (("f32", np.float32), ("f16", np.float16)):
+        rng = np.random.default_rng(12)
+        for t in z["lens"]:
+            t = int(t)
+            feat = rng.standard_normal((t, 16)).astype(dt)
+            sp, n = O.process_split(feat, 256)
+            assert n == int(z[f"{dt_name}:{t}:split_len"]) and sp.shape == z[f"{dt_name}:{t}:split"].shape
+            assert np.array_equal(sp, z[f"{dt_name}:{t}:split"])
+            pf, m = O.process_feat(feat, 256)
+            assert m == int(z[f"{dt_name}:{t}:feat_len"])
+            assert np.array_equal(np.asarray(pf, dtype=np.float32), np.asarray(z[f"{dt_name}:{t}:feat"], dtype=np.float32))
