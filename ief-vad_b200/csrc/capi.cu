@@ -124,7 +124,7 @@ int iefvad_model_forward(iefvad_model* m, const void* img, const void* ev, int i
 // first part's copy is exposed (the copy engine outruns the forward: ~18 k rows/ms over PCIe vs ~12 k rows/ms).
 static int forward_from_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
                              int64_t T, float* logits_host, float* scores_host, float* logits_dev, float* scores_dev,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int64_t* valid_len_host = nullptr, const int32_t* rowmap = nullptr) {
   IEF_CHECK(m && img_host && ev_host, "host-input forward: null argument");
   IEF_CHECK(in_dtype >= 0 && in_dtype <= 2, "unsupported input dtype code %d", in_dtype);
   IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
@@ -162,6 +162,9 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
   }
   for (auto& pp : m->host_in) for (auto& b : pp) IEF_TRY(b.reserve(rows * D * es));
   for (auto& b : m->host_out) IEF_TRY(b.reserve(rows * D * 4));
+  IEF_CHECK((valid_len_host == nullptr) == (rowmap == nullptr), "valid-rows mode needs both the host lengths and the device row map");
+  IEF_CHECK(valid_len_host == nullptr || (logits_host == nullptr && scores_host == nullptr),
+            "valid-rows mode returns compact DEVICE results");
   if (!logits_dev) IEF_TRY(m->host_logits.reserve(size_t(B) * T * 4));
   if (!scores_dev && scores_host) IEF_TRY(m->host_scores.reserve(size_t(B) * T * 4));
   float* ldev = logits_dev ? logits_dev : m->host_logits.as<float>();
@@ -171,10 +174,20 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
   IEF_CUDA(cudaEventRecord(m->ev_start, st));
   IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_start, 0));
   int64_t b0 = 0;
+  size_t j0 = 0;                       // compact output offset (valid-rows mode)
   for (int p = 0; p < int(partsB.size()); b0 += partsB[p], ++p) {
     const int buf = p & 1;
     const int64_t Bs = partsB[p];
     const size_t r0 = size_t(b0) * T, nr = size_t(Bs) * T;
+    ValidRows vr;
+    size_t nvalid = 0;
+    if (valid_len_host) {
+      for (int64_t b = b0; b < b0 + Bs; ++b) nvalid += size_t(valid_len_host[b] < 0 ? 0 : valid_len_host[b]);
+      vr.len_host = reinterpret_cast<const long long*>(valid_len_host) + b0;
+      vr.rowmap = rowmap + j0;
+      vr.row_base = static_cast<long long>(r0);
+    }
+    const size_t o0 = valid_len_host ? j0 : r0;
     if (p >= 2) IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_consumed[buf], 0));
     IEF_CUDA(cudaMemcpyAsync(m->host_in[buf][0].p, static_cast<const uint8_t*>(img_host) + r0 * D * es, nr * D * es,
                              cudaMemcpyHostToDevice, cs));
@@ -184,8 +197,9 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
     IEF_CUDA(cudaStreamWaitEvent(st, m->ev_copied[buf], 0));
     float* o[7];
     for (int i = 0; i < 7; ++i) o[i] = m->host_out[i].as<float>();
-    IEF_TRY(m->impl.forward(m->host_in[buf][0].p, m->host_in[buf][1].p, in_dtype, Bs, T, o[0], ldev + r0, o[1], o[2], o[3],
-                            o[4], o[5], o[6], sdev ? sdev + r0 : nullptr, st));
+    IEF_TRY(m->impl.forward(m->host_in[buf][0].p, m->host_in[buf][1].p, in_dtype, Bs, T, o[0], ldev + o0, o[1], o[2], o[3],
+                            o[4], o[5], o[6], sdev ? sdev + o0 : nullptr, st, valid_len_host ? &vr : nullptr));
+    j0 += nvalid;
     IEF_CUDA(cudaEventRecord(m->ev_consumed[buf], st));
     if (logits_host) IEF_CUDA(cudaMemcpyAsync(logits_host + r0, ldev + r0, nr * 4, cudaMemcpyDeviceToHost, st));
     if (scores_host) IEF_CUDA(cudaMemcpyAsync(scores_host + r0, sdev + r0, nr * 4, cudaMemcpyDeviceToHost, st));
@@ -207,6 +221,32 @@ int iefvad_model_forward_host_to_device(iefvad_model* m, const void* img_host, c
   IEF_CHECK(logits, "iefvad_model_forward_host_to_device: null logits");
   return forward_from_host(m, img_host, ev_host, in_dtype, B, T, nullptr, nullptr, logits, scores,
                            static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev, int in_dtype, int inputs_on_host,
+                                int64_t B, int64_t T, const int64_t* valid_len_host, const int32_t* rowmap,
+                                float* logits, float* scores, void* stream) {
+  IEF_CHECK(m && img && ev && logits, "iefvad_model_forward_scores: null argument");
+  IEF_CHECK(in_dtype >= 0 && in_dtype <= 2, "unsupported input dtype code %d", in_dtype);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (inputs_on_host)
+    return forward_from_host(m, img, ev, in_dtype, B, T, nullptr, nullptr, logits, scores, st, valid_len_host, rowmap);
+  IEF_CHECK((valid_len_host == nullptr) == (rowmap == nullptr), "valid-rows mode needs both the host lengths and the device row map");
+  IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
+  if (B == 0 || T == 0) return IEFVAD_OK;
+  size_t rows = size_t(B) * T;
+  ValidRows vr;
+  if (valid_len_host) {
+    rows = 0;
+    for (int64_t b = 0; b < B; ++b) rows += size_t(valid_len_host[b] < 0 ? 0 : valid_len_host[b]);
+    vr.len_host = reinterpret_cast<const long long*>(valid_len_host);
+    vr.rowmap = rowmap;
+  }
+  for (auto& b : m->host_out) IEF_TRY(b.reserve((rows ? rows : 1) * m->impl.D * 4));
+  float* o[7];
+  for (int i = 0; i < 7; ++i) o[i] = m->host_out[i].as<float>();
+  return m->impl.forward(img, ev, in_dtype, B, T, o[0], logits, o[1], o[2], o[3], o[4], o[5], o[6], scores, st,
+                         valid_len_host ? &vr : nullptr);
 }
 
 int iefvad_model_set_host_part_rows(iefvad_model* m, int64_t rows) {

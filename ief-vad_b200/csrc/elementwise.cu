@@ -180,6 +180,23 @@ fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, co
   }
 }
 
+// one warp per output row: 16-byte vectors, D % 8 == 0
+__global__ void __launch_bounds__(kThreads)
+gather_rows_kernel(const bf16* __restrict__ ctx, const float* __restrict__ x, const int* __restrict__ rowmap,
+                   long long row_base, long long n_rows, int D, bf16* __restrict__ ctx_c, float* __restrict__ x_c) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_rows; j += warps) {
+    const long long r = (long long)rowmap[j] - row_base;
+    const uint4* cs = reinterpret_cast<const uint4*>(ctx + r * D);
+    uint4* cd = reinterpret_cast<uint4*>(ctx_c + j * D);
+    for (int i = lane; i < D / 8; i += 32) cd[i] = cs[i];
+    const float4* xs = reinterpret_cast<const float4*>(x + r * D);
+    float4* xd = reinterpret_cast<float4*>(x_c + j * D);
+    for (int i = lane; i < D / 4; i += 32) xd[i] = xs[i];
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 to_half_kernel(const float* __restrict__ in, long long n, __half* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -269,6 +286,16 @@ int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* l
       reinterpret_cast<const float4*>(lv_i), reinterpret_cast<const float4*>(lv_e), n4, factor, eps,
       reinterpret_cast<float4*>(w_i), reinterpret_cast<float4*>(w_e), reinterpret_cast<float4*>(fused), fused_hi,
       fused_lo, hi_fp16);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long row_base, long long n_rows, int D,
+                bf16* ctx_c, float* x_c, int num_sms, cudaStream_t stream) {
+  IEF_CHECK(D % 8 == 0, "gather_rows: D=%d must be a multiple of 8", D);
+  if (n_rows == 0) return IEFVAD_OK;
+  gather_rows_kernel<<<grid_for(n_rows * 32, num_sms), kThreads, 0, stream>>>(ctx, x, rowmap, row_base, n_rows, D, ctx_c, x_c);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

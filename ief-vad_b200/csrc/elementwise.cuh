@@ -19,6 +19,10 @@ int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* l
          float eps, float* w_i, float* w_e, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
          cudaStream_t stream, int hi_fp16 = 0 /* fused_hi receives fp16 instead of bf16 */);
 
+// compact the rows listed in rowmap (minus row_base): ctx_c[j] = ctx[rowmap[j] - base] (16-bit rows), x_c[j] = x[...] (fp32)
+int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long row_base, long long n_rows, int D,
+                bf16* ctx_c, float* x_c, int num_sms, cudaStream_t stream);
+
 // fp32 -> fp16 (weights of the fp16-operand refinement GEMMs)
 int to_half(const float* in, long long n, void* out_f16, int num_sms, cudaStream_t stream);
 

@@ -245,7 +245,7 @@ int Model::reserve_workspace(long long rows, int B, int T, bool fp32_plan) {
 
 int Model::forward(const void* img, const void* ev, int in_dtype, long long B, long long T, float* fused, float* logits,
                    float* image_mu, float* event_mu, float* image_logvar, float* event_logvar, float* w_i, float* w_e,
-                   float* scores, cudaStream_t stream) {
+                   float* scores, cudaStream_t stream, const ValidRows* vr) {
   IEF_TRY(check_loaded());
   IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
   if (B == 0 || T == 0) return IEFVAD_OK;
@@ -253,6 +253,10 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
             "forward: null tensor pointer");
   IEF_CHECK(T <= (1 << 24), "T=%lld too long", T);
   const bool fp32_plan = plan < 0;
+  if (vr) {
+    IEF_CHECK(vr->len_host && vr->rowmap, "forward: valid-rows descriptor with null members");
+    IEF_CHECK(!fp32_plan && L >= 1, "forward: the valid-rows mode needs a tensor-core plan and at least one attention layer");
+  }
   const size_t in_esize = (in_dtype == IEFVAD_DT_F32) ? 4 : 2;
   long long slabB = max_rows / T;
   if (slabB < 1) slabB = 1;
@@ -270,6 +274,17 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     const long long M = (long long)Bs * T;
     IEF_CHECK(M < (1LL << 31), "slab of %lld rows exceeds 2^31", M);
     const long long row0 = b0 * T;
+    // valid-rows mode: Mo rows survive the last attention core; outputs are compact at offset `out0`
+    long long Mo = M, out0 = row0;
+    if (vr) {
+      out0 = 0;
+      for (long long b = 0; b < b0; ++b) out0 += vr->len_host[b];
+      Mo = 0;
+      for (long long b = b0; b < b0 + Bs; ++b) {
+        IEF_CHECK(vr->len_host[b] >= 0 && vr->len_host[b] <= T, "forward: valid length %lld outside [0, T]", vr->len_host[b]);
+        Mo += vr->len_host[b];
+      }
+    }
     for (int m = 0; m < 2; ++m) {
       const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + size_t(row0) * D * in_esize;
       const int e16 = (!fp32_plan && (plan & PLAN_FP16_ATTENTION)) ? 1 : 0;      // encoder operands in fp16
@@ -306,17 +321,30 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
           at.fp16 = a16; at.out_fp16 = a16;
           IEF_PROF(KC_ATTN_TC, 4.0 * M * T * D, attn_tc(at, stream));
-          EpiParams e2;
-          e2.bias = op.b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.out_f32 = y32.as<float>(); e2.ld_f32 = D;
-          GemmTcArgs g2;
-          g2.A_hi = h_hi.as<bf16>(); g2.W_hi = a16 ? op.w_h16 : op.w_hi; g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
-          g2.fp16 = a16;
-          IEF_PROF(KC_GEMM_OUT, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
-          // LN_i (+ whitening LN after the last layer, :117/:123); bf16 hi(/lo) feed the next GEMM
-          const bool need_lo = last ? (plan & PLAN_SPLIT_HEADS) != 0 : sp;
-          IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(y32.as<float>(), M, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
-                            last ? whiten_b[m] : nullptr, 1e-5f, last ? nullptr : x32.as<float>(), a_hi.as<bf16>(),
-                            need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream, (a16 && !last) ? 1 : 0));
+          // after the last attention core only the valid rows go on: gather (context, residual) into compact matrices
+          const bool compact = vr && last;
+          const long long Mc = compact ? Mo : M;
+          const bf16* ctx = h_hi.as<bf16>();
+          const float* resid = x32.as<float>();
+          float* yout = y32.as<float>();
+          if (compact) {
+            IEF_PROF(KC_GATHER, double(Mo) * D * 12, gather_rows(h_hi.as<bf16>(), x32.as<float>(), vr->rowmap + out0,
+                     vr->row_base + row0, Mo, D, h_lo.as<bf16>(), y32.as<float>(), num_sms, stream));
+            ctx = h_lo.as<bf16>(); resid = y32.as<float>(); yout = x32.as<float>();
+          }
+          if (Mc > 0) {
+            EpiParams e2;
+            e2.bias = op.b; e2.resid = resid; e2.ld_resid = D; e2.out_f32 = yout; e2.ld_f32 = D;
+            GemmTcArgs g2;
+            g2.A_hi = ctx; g2.W_hi = a16 ? op.w_h16 : op.w_hi; g2.M = int(Mc); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D;
+            g2.fp16 = a16;
+            IEF_PROF(KC_GEMM_OUT, 2.0 * Mc * D * D, gemm_tc(g2, e2, num_sms, stream));
+            // LN_i (+ whitening LN after the last layer, :117/:123); bf16 hi(/lo) feed the next GEMM
+            const bool need_lo = last ? (plan & PLAN_SPLIT_HEADS) != 0 : sp;
+            IEF_PROF(KC_LAYERNORM, double(Mc) * D * 8, layernorm(yout, Mc, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
+                              last ? whiten_b[m] : nullptr, 1e-5f, last ? nullptr : x32.as<float>(), a_hi.as<bf16>(),
+                              need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream, (a16 && !last) ? 1 : 0));
+          }
         }
       }
       if (L == 0) {
@@ -328,25 +356,27 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       }
       // heads (:125-128): one [M, D] x [2D, D]^T GEMM per modality, mu and logvar written to the user tensors
       EpiParams eh;
-      eh.bias = heads[m].b; eh.out_f32 = mu_out[m] + row0 * D; eh.out_f32_b = lv_out[m] + row0 * D; eh.ld_f32 = D;
+      eh.bias = heads[m].b; eh.out_f32 = mu_out[m] + out0 * D; eh.out_f32_b = lv_out[m] + out0 * D; eh.ld_f32 = D;
       eh.split_col = D;
+      if (Mo == 0) continue;
       if (fp32_plan) {
-        IEF_PROF(KC_GEMM_SIMT, 4.0 * M * D * D, gemm_simt(x32.as<float>(), D, heads[m].w, D, int(M), 2 * D, D, eh, stream));
+        IEF_PROF(KC_GEMM_SIMT, 4.0 * Mo * D * D, gemm_simt(x32.as<float>(), D, heads[m].w, D, int(Mo), 2 * D, D, eh, stream));
       } else {
         GemmTcArgs gh;
         gh.A_hi = a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>(); gh.W_hi = heads[m].w_hi; gh.W_lo = heads[m].w_lo;
-        gh.M = int(M); gh.N = 2 * D; gh.K = D; gh.lda = D; gh.ldw = D;
+        gh.M = int(Mo); gh.N = 2 * D; gh.K = D; gh.lda = D; gh.ldw = D;
         gh.nsplit = (plan & PLAN_SPLIT_HEADS) ? 3 : 1;
-        IEF_PROF(KC_GEMM_HEADS, 4.0 * M * D * D, gemm_tc(gh, eh, num_sms, stream));
+        IEF_PROF(KC_GEMM_HEADS, 4.0 * Mo * D * D, gemm_tc(gh, eh, num_sms, stream));
       }
     }
+    if (Mo == 0) continue;
     // uncertainty-weighted fusion (:130-144)
     const bool r16 = !fp32_plan && (plan & PLAN_FP16_REFINE);             // fp16 single-pass refinement operands
     const bool rsp = !fp32_plan && !r16 && (plan & PLAN_SPLIT_REFINE);
-    float* fused_out = fused + row0 * D;
+    float* fused_out = fused + out0 * D;
     float* xcur = (R == 0) ? fused_out : x32.as<float>();
-    IEF_PROF(KC_FUSE, double(M) * D * 28, fuse(image_mu + row0 * D, event_mu + row0 * D, image_logvar + row0 * D, event_logvar + row0 * D, M * D,
-                 factor, eps, w_i + row0 * D, w_e + row0 * D, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
+    IEF_PROF(KC_FUSE, double(Mo) * D * 28, fuse(image_mu + out0 * D, event_mu + out0 * D, image_logvar + out0 * D, event_logvar + out0 * D, Mo * D,
+                 factor, eps, w_i + out0 * D, w_e + out0 * D, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
                  (rsp && R > 0) ? a_lo.as<bf16>() : nullptr, num_sms, stream, r16 ? 1 : 0));
     // iterative refinement (:146-149): x <- x - lambda * (W2 relu(W1 x + b1) + b2)
     for (int i = 0; i < R; ++i) {
@@ -355,31 +385,31 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       if (fp32_plan) {
         EpiParams e1;
         e1.bias = ref1[i].b; e1.act = ACT_RELU; e1.out_f32 = h32.as<float>(); e1.ld_f32 = D;
-        IEF_PROF(KC_GEMM_SIMT, 2.0 * M * D * D, gemm_simt(x32.as<float>(), D, ref1[i].w, D, int(M), D, D, e1, stream));
+        IEF_PROF(KC_GEMM_SIMT, 2.0 * Mo * D * D, gemm_simt(x32.as<float>(), D, ref1[i].w, D, int(Mo), D, D, e1, stream));
         EpiParams e2;
         e2.bias = ref2[i].b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.alpha = -lambda_ref;
         e2.out_f32 = xnext; e2.ld_f32 = D;
-        IEF_PROF(KC_GEMM_SIMT, 2.0 * M * D * D, gemm_simt(h32.as<float>(), D, ref2[i].w, D, int(M), D, D, e2, stream));
+        IEF_PROF(KC_GEMM_SIMT, 2.0 * Mo * D * D, gemm_simt(h32.as<float>(), D, ref2[i].w, D, int(Mo), D, D, e2, stream));
       } else {
         EpiParams e1;
         e1.bias = ref1[i].b; e1.act = ACT_RELU; e1.out_hi = h_hi.as<bf16>(); e1.out_lo = rsp ? h_lo.as<bf16>() : nullptr;
         e1.ld_bf = D; e1.hi_fp16 = r16 ? 1 : 0;
         GemmTcArgs g1;
         g1.A_hi = a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = r16 ? ref1[i].w_h16 : ref1[i].w_hi; g1.W_lo = ref1[i].w_lo;
-        g1.M = int(M); g1.N = D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = rsp ? 3 : 1; g1.fp16 = r16 ? 1 : 0;
-        IEF_PROF(KC_GEMM_REF1, 2.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
+        g1.M = int(Mo); g1.N = D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = rsp ? 3 : 1; g1.fp16 = r16 ? 1 : 0;
+        IEF_PROF(KC_GEMM_REF1, 2.0 * Mo * D * D, gemm_tc(g1, e1, num_sms, stream));
         EpiParams e2;
         e2.bias = ref2[i].b; e2.resid = x32.as<float>(); e2.ld_resid = D; e2.alpha = -lambda_ref;
         e2.out_f32 = xnext; e2.ld_f32 = D;
         if (!last) { e2.out_hi = a_hi.as<bf16>(); e2.out_lo = rsp ? a_lo.as<bf16>() : nullptr; e2.ld_bf = D; e2.hi_fp16 = r16 ? 1 : 0; }
         GemmTcArgs g2;
         g2.A_hi = h_hi.as<bf16>(); g2.A_lo = h_lo.as<bf16>(); g2.W_hi = r16 ? ref2[i].w_h16 : ref2[i].w_hi; g2.W_lo = ref2[i].w_lo;
-        g2.M = int(M); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D; g2.nsplit = rsp ? 3 : 1; g2.fp16 = r16 ? 1 : 0;
-        IEF_PROF(KC_GEMM_REF2, 2.0 * M * D * D, gemm_tc(g2, e2, num_sms, stream));
+        g2.M = int(Mo); g2.N = D; g2.K = D; g2.lda = D; g2.ldw = D; g2.nsplit = rsp ? 3 : 1; g2.fp16 = r16 ? 1 : 0;
+        IEF_PROF(KC_GEMM_REF2, 2.0 * Mo * D * D, gemm_tc(g2, e2, num_sms, stream));
       }
     }
     // classifier (:150) stays fp32 in every plan
-    IEF_PROF(KC_CLASSIFIER, double(M) * D * 4, classifier(fused_out, M, D, cls_w, cls_b, logits + row0, scores ? scores + row0 : nullptr, num_sms, stream));
+    IEF_PROF(KC_CLASSIFIER, double(Mo) * D * 4, classifier(fused_out, Mo, D, cls_w, cls_b, logits + out0, scores ? scores + out0 : nullptr, num_sms, stream));
   }
   return IEFVAD_OK;
 }

@@ -48,6 +48,19 @@ struct ParamSlot {
   bool loaded = false;
 };
 
+// Optional "valid rows only" mode of the forward.  Callers that feed zero-padded chunks (data/tools.py:100-114) consume
+// only the first len rows of every batch element (train/ucf_test.py:112-114 `logits1[0:len_cur]`), but the pad rows
+// still act as attention KEYS.  With this descriptor the encoder runs on all rows up to and including the last
+// attention core; everything after it (out-projection, LayerNorms, heads, fusion, refinement, classifier - 65 % of
+// the FLOPs) runs on the valid rows only, gathered into a compact matrix.  Every output is then COMPACT
+// ([sum len, ...], valid row j of the whole call at index j) and bit-identical to the valid rows of the full forward.
+struct ValidRows {
+  const long long* len_host = nullptr;  // HOST [B]: valid rows (a prefix) of each batch element, 0 <= len <= T
+  const int* rowmap = nullptr;          // DEVICE [sum len]: row index (b * T + t, relative to this call's first row,
+                                        // after subtracting row_base) of every valid row, ascending
+  long long row_base = 0;               // subtracted from rowmap entries (lets a caller pass a slice of a global map)
+};
+
 struct Model {
   int D = 0, H = 0, L = 0, R = 0, dh = 0, dhp = 0;
   float lambda_ref = 0.5f, factor = 1.f, eps = 1e-8f;
@@ -80,13 +93,13 @@ struct Model {
   int reserve_workspace(long long rows, int B, int T, bool fp32_plan);
   int forward(const void* img, const void* ev, int in_dtype, long long B, long long T, float* fused, float* logits,
               float* image_mu, float* event_mu, float* image_logvar, float* event_logvar, float* w_i, float* w_e,
-              float* scores, cudaStream_t stream);
+              float* scores, cudaStream_t stream, const ValidRows* vr = nullptr);
   void destroy();
 };
 
 // Per-kernel-class device timing (CUDA events on the launching stream) for bench.py's roofline block.
 enum : int { KC_GEMM_QKV = 0, KC_ATTN_TC, KC_LAYERNORM, KC_FUSE, KC_CLASSIFIER, KC_INGEST, KC_GEMM_SIMT, KC_ATTN_SIMT,
-             KC_GEMM_OUT, KC_GEMM_HEADS, KC_GEMM_REF1, KC_GEMM_REF2, KC_COUNT };
+             KC_GEMM_OUT, KC_GEMM_HEADS, KC_GEMM_REF1, KC_GEMM_REF2, KC_GATHER, KC_COUNT };
 struct Profiler {
   bool on = false;
   struct Rec { int cls; double work; cudaEvent_t a, b; };   // work = algorithmic flops (GEMM/attn) or bytes (others)

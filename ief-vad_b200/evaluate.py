@@ -119,6 +119,19 @@ class Evaluator:
             mask[int(self.global_off[v]):int(self.global_off[v] + self.lengths[v])] = bits
         self.member = torch.as_tensor(mask.astype(np.uint32).view(np.int32), device=dev)
         self.num_subsets = 2 + len(self.class_keys)
+        # valid-rows mode: per chunk the number of real rows (a prefix; 0 for the all-zero chunk of a T % maxlen == 0
+        # video) and the row map b * maxlen + t of every real row - in video order, so the compact scores of the
+        # forward ARE the packed per-rank score vector (no compaction pass)
+        chunk_valid: List[int] = []
+        for v in self.mine:
+            T = int(self.lengths[v])
+            for k in range(num_chunks(T, maxlen)):
+                chunk_valid.append(max(0, min(maxlen, T - k * maxlen)))
+        self._chunk_valid = chunk_valid
+        rm = np.concatenate([np.arange(n_, dtype=np.int64) + c * maxlen for c, n_ in enumerate(chunk_valid)]
+                            ) if chunk_valid else np.zeros(0, dtype=np.int64)
+        self._rowmap = torch.as_tensor(rm.astype(np.int32), device=dev)
+        self.valid_rows_only = True
         self._img = self._ev = None
         self._pinned = None
 
@@ -147,6 +160,13 @@ class Evaluator:
         """Forward over all my chunks -> compacted sigmoid scores of my valid rows (device, fp32).  With host_inputs the
         pinned host features go through the library's pipelined host-input forward (copy overlapped with compute)."""
         packed = torch.empty(max(self.max_count, 1), dtype=torch.float32, device=self.device)
+        # (the fp32 FFMA plan has no valid-rows mode: it runs the full forward and compacts afterwards)
+        if self.local_chunks and self.valid_rows_only and str(self.model.temporal.precision) != "fp32":
+            img, ev = self._pinned if host_inputs else (self._img, self._ev)
+            out = self.model.temporal.scores(img, ev, self.device, self._chunk_valid, self._rowmap)
+            self._keep = out["_keepalive"]
+            packed[:self.my_rows].copy_(out["scores"])
+            return packed
         if self.local_chunks:
             if host_inputs:
                 out = self.model.temporal.scores_from_host(self._pinned[0], self._pinned[1], self.device)

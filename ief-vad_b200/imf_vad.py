@@ -157,33 +157,61 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         return out
 
 
-    def scores_from_host(self, img_host: torch.Tensor, ev_host: torch.Tensor, device) -> Dict[str, torch.Tensor]:
-        """Inference from HOST (ideally pinned) [B, T, D] inputs: the library pipelines the host->device copy with the
-        forward (iefvad_model_forward_host_to_device) and returns device `logits` [B, T, 1] and `scores` [B, T];
-        nothing waits for the device.  The host tensors must stay alive and unchanged until the stream has run."""
-        if img_host.is_cuda or ev_host.is_cuda:
-            raise RuntimeError("scores_from_host takes host tensors; use forward() for device tensors")
-        if img_host.dim() != 3 or img_host.shape != ev_host.shape or img_host.shape[-1] != self.embed_dim:
-            raise RuntimeError(f"expected two [B, T, {self.embed_dim}] host tensors")
+    def scores(self, img: torch.Tensor, ev: torch.Tensor, device=None, valid_lengths=None, rowmap=None
+               ) -> Dict[str, torch.Tensor]:
+        """Evaluation forward (iefvad_model_forward_scores): device `logits` / `scores` only.
+
+        img / ev: [B, T, D] on the device, or on the HOST (ideally pinned; `device` then names the GPU) - host inputs
+        go through the library's pipelined copy (part p+1 travels while part p computes); nothing waits for the device,
+        so host tensors must stay alive and unchanged until the stream has run.
+        valid_lengths (host int64 [B]) + rowmap (device int32 [sum len], b * T + t of every valid row): the "valid rows"
+        mode for zero-padded chunks - stages after the last attention core run on the valid rows only and the results
+        are COMPACT [sum len], bit-identical to the valid rows of the full forward."""
+        if img.dim() != 3 or img.shape != ev.shape or img.shape[-1] != self.embed_dim:
+            raise RuntimeError(f"expected two [B, T, {self.embed_dim}] tensors")
         codes = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
-        if img_host.dtype not in codes or ev_host.dtype != img_host.dtype:
-            raise RuntimeError("host inputs must share one of the dtypes float32 / float16 / bfloat16")
-        img, ev = img_host.contiguous(), ev_host.contiguous()
-        device = torch.device(device)
+        if img.dtype not in codes or ev.dtype != img.dtype:
+            raise RuntimeError("inputs must share one of the dtypes float32 / float16 / bfloat16")
+        on_host = not img.is_cuda
+        if on_host != (not ev.is_cuda):
+            raise RuntimeError("img and ev must both be on the host or both on the device")
+        device = torch.device(device) if on_host else img.device
+        if on_host and device.type != "cuda":
+            raise RuntimeError("host inputs need the target CUDA device")
+        img, ev = img.contiguous(), ev.contiguous()
         plan = _lib.PLANS.get(str(self.precision))
         if plan is None:
             raise ValueError(f"unknown precision plan {self.precision!r}; choose from {sorted(_lib.PLANS)}")
         B, T, _ = img.shape
+        if (valid_lengths is None) != (rowmap is None):
+            raise RuntimeError("valid_lengths and rowmap go together")
+        n_out, lens_ptr, keep = B * T, None, (img, ev)
+        if valid_lengths is not None:
+            import ctypes as C
+            lens = [int(v) for v in valid_lengths]
+            if len(lens) != B or rowmap.dtype != torch.int32 or not rowmap.is_cuda or rowmap.numel() != sum(lens):
+                raise RuntimeError("valid_lengths must have B entries and rowmap must be a device int32 tensor of sum(len)")
+            arr = (C.c_int64 * B)(*lens)
+            lens_ptr, n_out, keep = C.cast(arr, C.c_void_p), sum(lens), (img, ev, arr, rowmap)
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
             h = self._native(device)
             self._sync_params(h, device, stream)
             _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
-            logits = torch.empty((B, T, 1), dtype=torch.float32, device=device)
-            scores = torch.empty((B, T), dtype=torch.float32, device=device)
-            _lib.check(_lib.lib.iefvad_model_forward_host_to_device(
-                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], B, T, logits.data_ptr(), scores.data_ptr(), stream))
-        return {"logits": logits, "scores": scores, "_keepalive": (img, ev)}
+            logits = torch.empty(max(n_out, 1), dtype=torch.float32, device=device)[:n_out]
+            scores = torch.empty(max(n_out, 1), dtype=torch.float32, device=device)[:n_out]
+            _lib.check(_lib.lib.iefvad_model_forward_scores(
+                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], int(on_host), B, T, lens_ptr, _lib.ptr(rowmap),
+                logits.data_ptr(), scores.data_ptr(), stream))
+        if valid_lengths is None:
+            logits, scores = logits.view(B, T, 1), scores.view(B, T)
+        return {"logits": logits, "scores": scores, "_keepalive": keep}
+
+    def scores_from_host(self, img_host: torch.Tensor, ev_host: torch.Tensor, device) -> Dict[str, torch.Tensor]:
+        """Host-input evaluation forward on all rows (see `scores`)."""
+        if img_host.is_cuda or ev_host.is_cuda:
+            raise RuntimeError("scores_from_host takes host tensors; use forward() / scores() for device tensors")
+        return self.scores(img_host, ev_host, device)
 
 
 class MMFMIL(nn.Module):

@@ -97,6 +97,18 @@ int iefvad_model_forward_host_to_device(iefvad_model* m, const void* img_host, c
                                         int64_t B, int64_t T, float* logits, float* scores, void* stream);
 int iefvad_model_set_host_part_rows(iefvad_model* m, int64_t rows);
 
+/* Evaluation forward: only logits / scores are returned (the seven wide tensors stay in library scratch), from
+ * device inputs (inputs_on_host == 0) or through the pipelined host-input path (!= 0).
+ * Optional "valid rows" mode (both pointers non-NULL): callers that feed zero-padded chunks consume only the first
+ * len rows of each batch element (train/ucf_test.py:112-114 `logits1[0:len_cur]`) while the pad rows still act as
+ * attention keys.  valid_len_host: HOST int64 [B]; rowmap: DEVICE int32 [sum len] = b * T + t of every valid row,
+ * ascending.  The encoder then runs on all rows up to and including the last attention core; out-projection,
+ * LayerNorms, heads, fusion, refinement and classifier (65 %% of the FLOPs) run on the valid rows only, and
+ * logits / scores are COMPACT ([sum len]) - bit-identical to the valid rows of the full forward. */
+int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev, int in_dtype, int inputs_on_host,
+                                int64_t B, int64_t T, const int64_t* valid_len_host, const int32_t* rowmap,
+                                float* logits, float* scores, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone operators (device pointers) - the same kernels the forward uses, exposed for parity tests
  * ---------------------------------------------------------------------------------------------- */
@@ -238,10 +250,10 @@ uint64_t iefvad_launch_count(void);
 /* Per-kernel-class device timing of the model forward with CUDA events on the launching stream.
  * classes (IEFVAD_PROFILE_CLASSES = 12): 0 gemm_tc QKV in-projection, 1 attn_tc, 2 layernorm, 3 fuse, 4 classifier,
  * 5 ingest, 6 gemm_simt, 7 attn_simt, 8 gemm_tc out-projection, 9 gemm_tc heads, 10 gemm_tc refinement Linear 1
- * (ReLU), 11 gemm_tc refinement Linear 2 (residual).  iefvad_profile_read synchronises, fills ms / work (algorithmic
- * FLOPs for the GEMM and attention classes, algorithmic bytes otherwise) / launches (arrays of 12) for everything
+ * (ReLU), 11 gemm_tc refinement Linear 2 (residual), 12 valid-row gather.  iefvad_profile_read synchronises, fills ms / work (algorithmic
+ * FLOPs for the GEMM and attention classes, algorithmic bytes otherwise) / launches (arrays of 13) for everything
  * recorded since the last read, and clears the record. */
-#define IEFVAD_PROFILE_CLASSES 12
+#define IEFVAD_PROFILE_CLASSES 13
 int iefvad_profile_enable(int on);
 int iefvad_profile_read(double* ms, double* work, int64_t* launches);
 

@@ -244,3 +244,36 @@ def test_c5_long_sequence_t16384(pkg, full, plan):
     assert O.score_rel_err(out["logits"].cpu().numpy().reshape(-1), z["c5:logits"]) < SCORE_TOL[plan]
     rows = z["c1:rows"] * 64
     assert O.max_norm_err(out["fused"].cpu().numpy()[0, rows], z["c5:fused:rows"]) < TENSOR_TOL[plan]
+
+
+@pytest.mark.parametrize("plan", ["H", "B"])
+def test_valid_rows_mode_is_bit_identical_to_the_full_forward(pkg, full, plan):
+    """iefvad_model_forward_scores with a row map: stages after the last attention core run on the valid rows only;
+    the compact logits / scores equal the valid rows of the full forward bit for bit (device and host inputs,
+    including an all-zero chunk, a chunk with one valid row and slab / part boundaries)."""
+    from iefvad_b200 import _lib
+    _, synth = pkg
+    m, _ = full["full_default"]
+    m.temporal.precision = plan
+    vids = [synth.make_video(40 + i, T) for i, T in enumerate((300, 256, 1, 700, 255))]
+    ci = torch.cat([synth.chunk_video(v[0]) for v in vids])                 # [2 + 2 + 1 + 3 + 1, 256, 768]
+    ce = torch.cat([synth.chunk_video(v[1]) for v in vids])
+    valid = [256, 44, 256, 0, 1, 256, 256, 188, 255]
+    assert ci.shape[0] == len(valid)
+    rowmap = torch.cat([torch.arange(n) + c * 256 for c, n in enumerate(valid)]).to(torch.int32).cuda()
+    with torch.no_grad():
+        ref = m.temporal(ci.cuda(), ce.cuda(), with_scores=True)
+        sel = rowmap.long()
+        ref_s, ref_l = ref["scores"].reshape(-1)[sel], ref["logits"].reshape(-1)[sel]
+        out = m.temporal.scores(ci.cuda(), ce.cuda(), None, valid, rowmap)
+        assert torch.equal(out["scores"], ref_s) and torch.equal(out["logits"], ref_l)
+        for part_rows, max_rows in ((1024, 262144), (32768, 512), (2048, 768)):
+            _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, part_rows))
+            _lib.check(_lib.lib.iefvad_model_set_max_rows(m.temporal._handle, max_rows))
+            out = m.temporal.scores(ci.pin_memory(), ce.pin_memory(), torch.device("cuda", 0), valid, rowmap)
+            torch.cuda.synchronize()
+            assert torch.equal(out["scores"], ref_s) and torch.equal(out["logits"], ref_l), (part_rows, max_rows)
+            out = m.temporal.scores(ci.cuda(), ce.cuda(), None, valid, rowmap)
+            assert torch.equal(out["scores"], ref_s), (part_rows, max_rows)
+        _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, 32768))
+        _lib.check(_lib.lib.iefvad_model_set_max_rows(m.temporal._handle, 262144))
