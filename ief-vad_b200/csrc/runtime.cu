@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "tensormap.cuh"
@@ -45,8 +46,55 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs ~1 us on the host and a forward issues ~270 of them, always for the same few dozen
+// (pointer, shape) combinations (the workspace is stable across calls): memoise the 128-byte descriptors.
+namespace {
+struct TmKey {
+  uint64_t v[12];
+  bool operator==(const TmKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmHash {
+  size_t operator()(const TmKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return size_t(h);
+  }
+};
+std::mutex g_tm_mutex;
+std::unordered_map<TmKey, CUtensorMap, TmHash> g_tm_cache;
+}  // namespace
+
+static int encode_uncached(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims,
+                           const cuuint64_t* strides, const cuuint32_t* box, int dtype, int swizzle);
+
 static int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims, const cuuint64_t* strides,
                   const cuuint32_t* box, int dtype, int swizzle) {
+  TmKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = reinterpret_cast<uint64_t>(base);
+  key.v[1] = (uint64_t(rank) << 32) | (uint64_t(uint32_t(dtype)) << 8) | uint64_t(uint32_t(swizzle));
+  for (uint32_t i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[6 + i] = (i + 1 < rank) ? strides[i] : 0;
+    key.v[10 + i / 2] |= uint64_t(box[i]) << (32 * (i & 1));
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_tm_mutex);
+    auto it = g_tm_cache.find(key);
+    if (it != g_tm_cache.end()) {
+      *out = it->second;
+      return IEFVAD_OK;
+    }
+  }
+  IEF_TRY(encode_uncached(out, base, rank, dims, strides, box, dtype, swizzle));
+  std::lock_guard<std::mutex> lock(g_tm_mutex);
+  if (g_tm_cache.size() > 65536) g_tm_cache.clear();      // pointers of short-lived tensors: bound the table
+  g_tm_cache.emplace(key, *out);
+  return IEFVAD_OK;
+}
+
+static int encode_uncached(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims,
+                           const cuuint64_t* strides, const cuuint32_t* box, int dtype, int swizzle) {
   auto fn = get_encode();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
