@@ -9,6 +9,8 @@
 //           fp32 registers with the online-softmax rescale.  Optional additive mask / key-padding mask serve
 //           the model/module.py block (D4).
 // attn_simt : fp32 reference plan (one warp per query row), same math in IEEE fp32.
+#include <cstdlib>
+
 #include "attention.cuh"
 #include "common.cuh"
 #include "tensormap.cuh"
@@ -403,7 +405,8 @@ int attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
   IEF_CHECK(a.Tpad % 8 == 0 && a.Tpad >= a.T, "attn_tc: Tpad=%d must be a multiple of 8 and >= T=%d", a.Tpad, a.T);
   IEF_CHECK(a.ldo % 8 == 0, "attn_tc: ldo must be a multiple of 8");
   IEF_CHECK(a.B <= 65535 && a.H <= 65535, "attn_tc: B=%d / H=%d exceed the grid limits", a.B, a.H);
-  const int kb = a.key_block ? a.key_block : (a.T <= 2048 ? 64 : 128);
+  static const int env_kb = [] { const char* e = getenv("IEFVAD_ATTN_KB"); return e ? atoi(e) : 0; }();   // tuning knob
+  const int kb = a.key_block ? a.key_block : (env_kb ? env_kb : (a.T <= 2048 ? 64 : 128));
   IEF_CHECK(kb == 64 || kb == 128, "attn_tc: key_block must be 64 or 128");
 #define IEF_ATTN(DH_, DHP_)                                                      \
   if (a.dh == DH_ && a.dhp == DHP_)                                              \
