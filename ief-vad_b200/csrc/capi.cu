@@ -2,6 +2,7 @@
 #include "../../include/iefvad.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -124,19 +125,25 @@ int iefvad_model_forward(iefvad_model* m, const void* img, const void* ev, int i
 // first part's copy is exposed (the copy engine outruns the forward: ~18 k rows/ms over PCIe vs ~12 k rows/ms).
 static int forward_from_host(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype, int64_t B,
                              int64_t T, float* logits_host, float* scores_host, float* logits_dev, float* scores_dev,
-                             cudaStream_t st, const int64_t* valid_len_host = nullptr, const int32_t* rowmap = nullptr) {
+                             cudaStream_t st, const int64_t* valid_len_host = nullptr, const int32_t* rowmap = nullptr,
+                             const int64_t* chunk_start_dev = nullptr, const int32_t* chunk_valid_dev = nullptr) {
   IEF_CHECK(m && img_host && ev_host, "host-input forward: null argument");
   IEF_CHECK(in_dtype >= 0 && in_dtype <= 2, "unsupported input dtype code %d", in_dtype);
   IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
   if (B == 0 || T == 0) return IEFVAD_OK;
   const int D = m->impl.D;
   const size_t es = (in_dtype == IEFVAD_F32) ? 4 : 2;
-  // Part sizes grow geometrically (x 1.4, the copy engine's lead over the forward) from host_part_rows / 4: a small
-  // first part keeps the exposed copy short, large later parts keep the GEMM grids full.
+  // Part sizes grow geometrically from a small first part (short exposed copy) to large later parts (full GEMM grids):
+  // x 1.4 from host_part_rows / 4 for dense chunks (the copy engine leads the forward by about that factor), x 3 from
+  // host_part_rows / 8 for ragged inputs (no pad rows on the wire: the copy is twice as fast as the forward).
   const int64_t cap_rows = m->impl.max_rows;
   std::vector<int64_t> partsB;
   {
-    double want = double(m->host_part_rows) / 4.0;
+    static const double env_first = [] { const char* e = getenv("IEFVAD_HOST_PART_FIRST"); return e ? atof(e) : 0.0; }();
+    static const double env_growth = [] { const char* e = getenv("IEFVAD_HOST_PART_GROWTH"); return e ? atof(e) : 0.0; }();
+    const bool ragged_in = chunk_start_dev != nullptr;
+    const double growth = env_growth > 1.0 ? env_growth : (ragged_in ? 3.0 : 1.4);
+    double want = env_first > 0.0 ? env_first : double(m->host_part_rows) / (ragged_in ? 8.0 : 4.0);
     int64_t left = B;
     while (left > 0) {
       int64_t pb = int64_t(want / double(T));
@@ -146,7 +153,7 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
       if (pb * T > cap_rows && left > pb) pb = left;         // (keeps the invariant below simple)
       partsB.push_back(pb);
       left -= pb;
-      want *= 1.4;
+      want *= growth;
     }
   }
   int64_t maxB = 0;
@@ -165,6 +172,9 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
   IEF_CHECK((valid_len_host == nullptr) == (rowmap == nullptr), "valid-rows mode needs both the host lengths and the device row map");
   IEF_CHECK(valid_len_host == nullptr || (logits_host == nullptr && scores_host == nullptr),
             "valid-rows mode returns compact DEVICE results");
+  const bool ragged = chunk_start_dev != nullptr;
+  IEF_CHECK((chunk_start_dev == nullptr) == (chunk_valid_dev == nullptr), "ragged inputs need chunk_start and chunk_valid");
+  IEF_CHECK(!ragged || valid_len_host, "ragged inputs need the valid-rows descriptors");
   if (!logits_dev) IEF_TRY(m->host_logits.reserve(size_t(B) * T * 4));
   if (!scores_dev && scores_host) IEF_TRY(m->host_scores.reserve(size_t(B) * T * 4));
   float* ldev = logits_dev ? logits_dev : m->host_logits.as<float>();
@@ -189,10 +199,19 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
     }
     const size_t o0 = valid_len_host ? j0 : r0;
     if (p >= 2) IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_consumed[buf], 0));
-    IEF_CUDA(cudaMemcpyAsync(m->host_in[buf][0].p, static_cast<const uint8_t*>(img_host) + r0 * D * es, nr * D * es,
-                             cudaMemcpyHostToDevice, cs));
-    IEF_CUDA(cudaMemcpyAsync(m->host_in[buf][1].p, static_cast<const uint8_t*>(ev_host) + r0 * D * es, nr * D * es,
-                             cudaMemcpyHostToDevice, cs));
+    // ragged: the host buffers hold only the valid rows, chunk after chunk - this part's rows are [j0, j0 + nvalid)
+    const size_t src0 = ragged ? j0 : r0, nsrc = ragged ? nvalid : nr;
+    if (ragged) {
+      vr.chunk_start = reinterpret_cast<const long long*>(chunk_start_dev) + b0;
+      vr.chunk_valid = chunk_valid_dev + b0;
+      vr.start_base = static_cast<long long>(j0);
+    }
+    if (nsrc) {
+      IEF_CUDA(cudaMemcpyAsync(m->host_in[buf][0].p, static_cast<const uint8_t*>(img_host) + src0 * D * es, nsrc * D * es,
+                               cudaMemcpyHostToDevice, cs));
+      IEF_CUDA(cudaMemcpyAsync(m->host_in[buf][1].p, static_cast<const uint8_t*>(ev_host) + src0 * D * es, nsrc * D * es,
+                               cudaMemcpyHostToDevice, cs));
+    }
     IEF_CUDA(cudaEventRecord(m->ev_copied[buf], cs));
     IEF_CUDA(cudaStreamWaitEvent(st, m->ev_copied[buf], 0));
     float* o[7];
@@ -221,6 +240,16 @@ int iefvad_model_forward_host_to_device(iefvad_model* m, const void* img_host, c
   IEF_CHECK(logits, "iefvad_model_forward_host_to_device: null logits");
   return forward_from_host(m, img_host, ev_host, in_dtype, B, T, nullptr, nullptr, logits, scores,
                            static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_model_forward_scores_ragged(iefvad_model* m, const void* img_packed_host, const void* ev_packed_host,
+                                       int in_dtype, int64_t B, int64_t T, const int64_t* valid_len_host,
+                                       const int32_t* rowmap, const int64_t* chunk_start, const int32_t* chunk_valid,
+                                       float* logits, float* scores, void* stream) {
+  IEF_CHECK(m && img_packed_host && ev_packed_host && logits && valid_len_host && rowmap && chunk_start && chunk_valid,
+            "iefvad_model_forward_scores_ragged: null argument");
+  return forward_from_host(m, img_packed_host, ev_packed_host, in_dtype, B, T, nullptr, nullptr, logits, scores,
+                           static_cast<cudaStream_t>(stream), valid_len_host, rowmap, chunk_start, chunk_valid);
 }
 
 int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev, int in_dtype, int inputs_on_host,

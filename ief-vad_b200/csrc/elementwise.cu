@@ -77,6 +77,40 @@ ingest_kernel(const Tin* __restrict__ in, long long n8, float* __restrict__ out_
   }
 }
 
+// ragged ingest: row (c, t) of the zero-padded [n_chunks, T, D] batch comes from packed[chunk_start[c] - base + t] when
+// t < chunk_valid[c] and is zero otherwise - process_split (data/tools.py:100-114) folded into the ingest, so the
+// pad rows never cross PCIe nor get read from HBM
+template <typename Tin>
+__global__ void __launch_bounds__(kThreads)
+ingest_ragged_kernel(const Tin* __restrict__ packed, const long long* __restrict__ chunk_start, long long start_base,
+                     const int* __restrict__ chunk_valid, long long n8, int T, int D8, float* __restrict__ out_f32,
+                     bf16* __restrict__ out_hi, int hi_fp16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / D8;
+    const int col8 = int(i - row * D8);
+    const long long c = row / T;
+    const int t = int(row - c * T);
+    float v[8];
+    if (t < chunk_valid[c]) {
+      load8<Tin>(packed + ((chunk_start[c] - start_base + t) * D8 + col8) * 8, v);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    }
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + i * 8);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (out_hi) {
+      uint4 u;
+      u.x = pack_16x2(v[0], v[1], hi_fp16); u.y = pack_16x2(v[2], v[3], hi_fp16);
+      u.z = pack_16x2(v[4], v[5], hi_fp16); u.w = pack_16x2(v[6], v[7], hi_fp16);
+      *reinterpret_cast<uint4*>(out_hi + i * 8) = u;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- LayerNorm: one warp per row, row in registers
 template <int NV>   // D = 128 * NV
 __global__ void __launch_bounds__(kThreads)
@@ -249,6 +283,35 @@ int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi,
       break;
     default:
       set_error("ingest: unsupported dtype code %d (0 = f32, 1 = f16, 2 = bf16)", dtype);
+      return IEFVAD_ERR_INVALID;
+  }
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int ingest_ragged(const void* packed, int dtype, const long long* chunk_start, long long start_base, const int* chunk_valid,
+                  long long n_chunks, int T, int D, float* out_f32, bf16* out_hi, int hi_fp16, int num_sms,
+                  cudaStream_t stream) {
+  IEF_CHECK(D % 8 == 0, "ingest_ragged: D=%d must be a multiple of 8", D);
+  if (n_chunks == 0 || T == 0) return IEFVAD_OK;
+  const long long n8 = n_chunks * T * (D / 8);
+  const int grid = grid_for(n8, num_sms);
+  switch (dtype) {
+    case IEFVAD_DT_F32:
+      ingest_ragged_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(packed), chunk_start, start_base,
+                                                                  chunk_valid, n8, T, D / 8, out_f32, out_hi, hi_fp16);
+      break;
+    case IEFVAD_DT_F16:
+      ingest_ragged_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half*>(packed), chunk_start, start_base,
+                                                                   chunk_valid, n8, T, D / 8, out_f32, out_hi, hi_fp16);
+      break;
+    case IEFVAD_DT_BF16:
+      ingest_ragged_kernel<bf16><<<grid, kThreads, 0, stream>>>(static_cast<const bf16*>(packed), chunk_start, start_base,
+                                                                 chunk_valid, n8, T, D / 8, out_f32, out_hi, hi_fp16);
+      break;
+    default:
+      set_error("ingest_ragged: unsupported dtype code %d", dtype);
       return IEFVAD_ERR_INVALID;
   }
   count_launches(1);

@@ -9,6 +9,12 @@ enum : int { IEFVAD_DT_F32 = 0, IEFVAD_DT_F16 = 1, IEFVAD_DT_BF16 = 2 };
 int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms,
            cudaStream_t stream, int hi_fp16 = 0 /* out_hi receives fp16 instead of bf16 (no lo) */);
 
+// The same for a ragged batch: `packed` holds only the valid rows of the n_chunks zero-padded [T, D] chunks, chunk c's
+// rows starting at packed row chunk_start[c] - start_base (device arrays); pad rows are written as zeros.
+int ingest_ragged(const void* packed, int dtype, const long long* chunk_start, long long start_base, const int* chunk_valid,
+                  long long n_chunks, int T, int D, float* out_f32, bf16* out_hi, int hi_fp16, int num_sms,
+                  cudaStream_t stream);
+
 // out = LN(x; w1, b1) or LN(LN(x; w1, b1); w2, b2) when w2 != null.  x [M, D] fp32.
 int layernorm(const float* x, long long M, int D, const float* w1, const float* b1, const float* w2, const float* b2,
               float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream,

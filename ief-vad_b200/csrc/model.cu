@@ -286,9 +286,16 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       }
     }
     for (int m = 0; m < 2; ++m) {
-      const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + size_t(row0) * D * in_esize;
+      const bool ragged = vr && vr->chunk_start && vr->chunk_valid;
+      const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + (ragged ? 0 : size_t(row0) * D * in_esize);
       const int e16 = (!fp32_plan && (plan & PLAN_FP16_ATTENTION)) ? 1 : 0;      // encoder operands in fp16
       const bool esp = !fp32_plan && !e16 && (plan & PLAN_SPLIT_ENCODER);
+      if (ragged) {
+        IEF_CHECK(!esp, "forward: ragged inputs are not combined with the split-encoder plan");
+        IEF_PROF(KC_INGEST, double(Mo) * D * in_esize + double(M) * D * (4 + 2),
+                 ingest_ragged(in, in_dtype, vr->chunk_start + b0, vr->start_base, vr->chunk_valid + b0, Bs, int(T), D,
+                               x32.as<float>(), a_hi.as<bf16>(), (e16 && L > 0) ? 1 : 0, num_sms, stream));
+      } else
       IEF_PROF(KC_INGEST, double(M) * D * (in_esize + 4 + 2), ingest(in, in_dtype, M * D, x32.as<float>(), fp32_plan ? nullptr : a_hi.as<bf16>(),
                      esp ? a_lo.as<bf16>() : nullptr, num_sms, stream, (e16 && L > 0) ? 1 : 0));
       for (int i = 0; i < L; ++i) {                                   // model/imf_vad.py:114-116 / :120-122

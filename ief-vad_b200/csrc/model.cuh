@@ -59,6 +59,11 @@ struct ValidRows {
   const int* rowmap = nullptr;          // DEVICE [sum len]: row index (b * T + t, relative to this call's first row,
                                         // after subtracting row_base) of every valid row, ascending
   long long row_base = 0;               // subtracted from rowmap entries (lets a caller pass a slice of a global map)
+  // ragged inputs (optional, both non-null): img / ev then point at PACKED device buffers that hold only the valid rows
+  // (chunk b's rows start at packed row chunk_start[b] - start_base); the pad rows are synthesised as zeros on ingest
+  const long long* chunk_start = nullptr;   // DEVICE [B]
+  const int* chunk_valid = nullptr;         // DEVICE [B] (== len_host)
+  long long start_base = 0;
 };
 
 struct Model {

@@ -131,6 +131,11 @@ class Evaluator:
         rm = np.concatenate([np.arange(n_, dtype=np.int64) + c * maxlen for c, n_ in enumerate(chunk_valid)]
                             ) if chunk_valid else np.zeros(0, dtype=np.int64)
         self._rowmap = torch.as_tensor(rm.astype(np.int32), device=dev)
+        cv = np.asarray(chunk_valid, dtype=np.int64)
+        self._chunk_start = torch.as_tensor(np.concatenate([[0], np.cumsum(cv)])[:-1].astype(np.int64) if len(cv) else
+                                            np.zeros(0, dtype=np.int64), device=dev)
+        self._chunk_valid_dev = torch.as_tensor(cv.astype(np.int32), device=dev)
+        self._ragged = None
         self.valid_rows_only = True
         self._img = self._ev = None
         self._pinned = None
@@ -155,6 +160,22 @@ class Evaluator:
                         ev_chunks if ev_chunks.is_pinned() else ev_chunks.pin_memory())
         self._img = self._ev = None
 
+    def set_host_ragged(self, feats_img: Sequence[torch.Tensor], feats_ev: Sequence[torch.Tensor],
+                        dtype=torch.float16) -> None:
+        """Pinned host staging of my videos' RAW [T_v, D] features back to back (what the .npy files hold): the
+        end-to-end path then copies only real rows; the chunk / zero-pad rule is applied on the device (row N2)."""
+        def pack(feats):
+            rows = [torch.nan_to_num(f, nan=0.0).to(dtype) for f in feats]             # train/ucf_test.py:83-88
+            out = torch.empty((self.my_rows, self.model.embed_dim), dtype=dtype, pin_memory=True)
+            if rows:
+                torch.cat(rows, out=out)
+            return out
+        if [int(f.shape[0]) for f in feats_img] != [int(self.lengths[v]) for v in self.mine]:
+            raise ValueError("features do not match this rank's video lengths")
+        self._ragged = (pack(feats_img), pack(feats_ev))
+        self._pinned = None
+        self._img = self._ev = None
+
     # ------------------------------------------------------------------ one evaluation pass
     def local_scores(self, host_inputs: bool = False) -> torch.Tensor:
         """Forward over all my chunks -> compacted sigmoid scores of my valid rows (device, fp32).  With host_inputs the
@@ -162,8 +183,13 @@ class Evaluator:
         packed = torch.empty(max(self.max_count, 1), dtype=torch.float32, device=self.device)
         # (the fp32 FFMA plan has no valid-rows mode: it runs the full forward and compacts afterwards)
         if self.local_chunks and self.valid_rows_only and str(self.model.temporal.precision) != "fp32":
-            img, ev = self._pinned if host_inputs else (self._img, self._ev)
-            out = self.model.temporal.scores(img, ev, self.device, self._chunk_valid, self._rowmap)
+            if host_inputs and self._ragged is not None:
+                out = self.model.temporal.scores_ragged(self._ragged[0], self._ragged[1], self.device, self.maxlen,
+                                                        self._chunk_valid, self._rowmap, self._chunk_start,
+                                                        self._chunk_valid_dev)
+            else:
+                img, ev = self._pinned if host_inputs else (self._img, self._ev)
+                out = self.model.temporal.scores(img, ev, self.device, self._chunk_valid, self._rowmap)
             self._keep = out["_keepalive"]
             packed[:self.my_rows].copy_(out["scores"])
             return packed
@@ -228,6 +254,8 @@ class Evaluator:
 
     # bytes moved by a host-input step (for bench.py's e2e block)
     def h2d_bytes(self) -> int:
+        if self._ragged is not None:
+            return 2 * self._ragged[0].numel() * self._ragged[0].element_size()
         return 2 * self.local_chunks * self.maxlen * self.model.embed_dim * (self._pinned[0].element_size()
                                                                              if self._pinned else 2)
 

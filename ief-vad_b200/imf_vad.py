@@ -207,6 +207,43 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             logits, scores = logits.view(B, T, 1), scores.view(B, T)
         return {"logits": logits, "scores": scores, "_keepalive": keep}
 
+    def scores_ragged(self, img_packed: torch.Tensor, ev_packed: torch.Tensor, device, T: int, valid_lengths, rowmap,
+                      chunk_start, chunk_valid) -> Dict[str, torch.Tensor]:
+        """Evaluation forward from RAGGED host features (iefvad_model_forward_scores_ragged): img_packed / ev_packed are
+        HOST (pinned) [sum len, D] tensors holding only the valid rows of the zero-padded [T, D] chunks, chunk after
+        chunk; the chunk / pad rule of data/tools.py:100-114 is applied on the device while ingesting.  valid_lengths:
+        host ints [B]; rowmap (int32), chunk_start (int64), chunk_valid (int32): device tensors.  Compact results."""
+        import ctypes as C
+        codes = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+        lens = [int(v) for v in valid_lengths]
+        B, n = len(lens), sum(int(v) for v in valid_lengths)
+        if img_packed.is_cuda or ev_packed.is_cuda or img_packed.shape != ev_packed.shape or img_packed.dtype != ev_packed.dtype:
+            raise RuntimeError("scores_ragged takes two host tensors of the same shape and dtype")
+        if tuple(img_packed.shape) != (n, self.embed_dim) or img_packed.dtype not in codes:
+            raise RuntimeError(f"packed features must be [{n}, {self.embed_dim}] float32 / float16 / bfloat16")
+        if any(v < 0 or v > T for v in lens):
+            raise RuntimeError("valid lengths must lie in [0, T]")
+        device = torch.device(device)
+        for t, dt, cnt in ((rowmap, torch.int32, n), (chunk_start, torch.int64, B), (chunk_valid, torch.int32, B)):
+            if not t.is_cuda or t.dtype != dt or t.numel() != cnt:
+                raise RuntimeError("rowmap / chunk_start / chunk_valid must be device tensors (int32 [sum len], int64 [B], int32 [B])")
+        plan = _lib.PLANS.get(str(self.precision))
+        if plan is None:
+            raise ValueError(f"unknown precision plan {self.precision!r}; choose from {sorted(_lib.PLANS)}")
+        img, ev = img_packed.contiguous(), ev_packed.contiguous()
+        arr = (C.c_int64 * B)(*lens)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            h = self._native(device)
+            self._sync_params(h, device, stream)
+            _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
+            logits = torch.empty(max(n, 1), dtype=torch.float32, device=device)[:n]
+            scores = torch.empty(max(n, 1), dtype=torch.float32, device=device)[:n]
+            _lib.check(_lib.lib.iefvad_model_forward_scores_ragged(
+                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], B, T, C.cast(arr, C.c_void_p), rowmap.data_ptr(),
+                chunk_start.data_ptr(), chunk_valid.data_ptr(), logits.data_ptr(), scores.data_ptr(), stream))
+        return {"logits": logits, "scores": scores, "_keepalive": (img, ev, arr, rowmap, chunk_start, chunk_valid)}
+
     def scores_from_host(self, img_host: torch.Tensor, ev_host: torch.Tensor, device) -> Dict[str, torch.Tensor]:
         """Host-input evaluation forward on all rows (see `scores`)."""
         if img_host.is_cuda or ev_host.is_cuda:

@@ -109,6 +109,17 @@ int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev
                                 int64_t B, int64_t T, const int64_t* valid_len_host, const int32_t* rowmap,
                                 float* logits, float* scores, void* stream);
 
+/* The evaluation forward from RAGGED pinned host features: img_packed_host / ev_packed_host hold only the valid rows
+ * of the B zero-padded [T, D] chunks, chunk after chunk (i.e. the videos' [T_v, D] arrays back to back, as the .npy
+ * files hold them) - process_split (data/tools.py:100-114) happens on the device inside the ingest kernel, so the
+ * pad rows neither cross PCIe nor are read from HBM.  valid_len_host / rowmap as for iefvad_model_forward_scores;
+ * chunk_start: DEVICE int64 [B] = exclusive prefix sums of the valid lengths; chunk_valid: DEVICE int32 [B].
+ * Pipelined like the other host-input calls; logits / scores are compact DEVICE vectors [sum len]. */
+int iefvad_model_forward_scores_ragged(iefvad_model* m, const void* img_packed_host, const void* ev_packed_host,
+                                       int in_dtype, int64_t B, int64_t T, const int64_t* valid_len_host,
+                                       const int32_t* rowmap, const int64_t* chunk_start, const int32_t* chunk_valid,
+                                       float* logits, float* scores, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone operators (device pointers) - the same kernels the forward uses, exposed for parity tests
  * ---------------------------------------------------------------------------------------------- */

@@ -275,5 +275,14 @@ def test_valid_rows_mode_is_bit_identical_to_the_full_forward(pkg, full, plan):
             assert torch.equal(out["scores"], ref_s) and torch.equal(out["logits"], ref_l), (part_rows, max_rows)
             out = m.temporal.scores(ci.cuda(), ce.cuda(), None, valid, rowmap)
             assert torch.equal(out["scores"], ref_s), (part_rows, max_rows)
+            # ragged host inputs: only the valid rows travel, the pad rows are synthesised on the device
+            packed_i = torch.cat([v[0] for v in vids]).pin_memory()
+            packed_e = torch.cat([v[1] for v in vids]).pin_memory()
+            cv = torch.tensor(valid)
+            cstart = (torch.cumsum(cv, 0) - cv).to(torch.int64).cuda()
+            out = m.temporal.scores_ragged(packed_i, packed_e, torch.device("cuda", 0), 256, valid, rowmap, cstart,
+                                           cv.to(torch.int32).cuda())
+            torch.cuda.synchronize()
+            assert torch.equal(out["scores"], ref_s) and torch.equal(out["logits"], ref_l), ("ragged", part_rows, max_rows)
         _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, 32768))
         _lib.check(_lib.lib.iefvad_model_set_max_rows(m.temporal._handle, 262144))
