@@ -485,7 +485,7 @@ def main():
     value = frames_total / (ms_dev * 1e-3)
     e2e_val = frames_total / (ms_e2e * 1e-3)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N = 1 only
         v, ms, cores, sample = cpu_port_run(build_workload(args.workload, 0, 1, synth), args.cpu_sample, 1, 1, synth)
         cpu = {"value": round(v, 1), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
     line = {

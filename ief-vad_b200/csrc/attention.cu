@@ -22,6 +22,13 @@ namespace {
 constexpr int QB = 128;   // query rows per CTA
 constexpr float kLog2e = 1.4426950408889634f;
 
+// 2^x on the SFU in one instruction (ex2.approx.ftz: 2 ulp, flushes denormal results - they vanish in the 16-bit P)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // KB = keys per block.  KB = 64 halves every per-CTA resource (104 KB smem, 256 TMEM columns) so that TWO CTAs share
 // an SM and one CTA's softmax overlaps the other's MMAs / loads - the short-sequence configuration (T_c = 256 has
 // only two 128-key blocks to pipeline within a CTA); KB = 128 halves the per-key synchronisation for long T.
@@ -164,6 +171,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int tq = qt * QB + r;
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
     float m = -INFINITY, l = 0.f;
+    float alpha_prev = 0.f;       // rescale factor of the previous block: applied when that block's P.V is folded in
     float o_acc[DH];
 #pragma unroll
     for (int d = 0; d < DH; ++d) o_acc[d] = 0.f;
@@ -202,7 +210,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
         }
       }
-      // ---- fold the previous block's P.V into the register accumulator (also frees P smem)
+      // ---- fold the previous block's P.V into the register accumulator (also frees P smem).  The accumulator is
+      // kept relative to the max BEFORE the previous block; one FFMA per element rescales it and adds the block.
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
@@ -212,19 +221,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_ld32(tmem_base + Cfg::kOffO + lane_off + uint32_t(c * 32), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += v[i];
+          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, v[i]);
         }
         tc_fence_before();
         mbar_arrive(o_empty);
       }
       // a fully masked prefix keeps mx == -inf: use 0 as the reference point so exp2 stays finite
       const float mref = (mx == -INFINITY) ? 0.f : mx;
-      const float alpha = exp2f((m - mref) * kLog2e);   // m == -inf -> 0
+      const float alpha = fast_exp2((m - mref) * kLog2e);   // m == -inf -> 0
       m = mx;
       l *= alpha;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) o_acc[d] *= alpha;
-      // ---- pass 2: P = exp(S - m) -> bf16, swizzled K-major smem (A operand of P.V)
+      alpha_prev = alpha;
+      // ---- pass 2: P = exp(S - m) -> 16-bit, swizzled K-major smem (A operand of P.V)
       const float mscaled = mref * kLog2e;
       float lsum = 0.f;
 #pragma unroll 1
@@ -243,7 +251,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               if (prow && prow[key]) x = -INFINITY;
             }
           }
-          const float p = exp2f(fmaf(x, kLog2e, -mscaled));
+          const float p = fast_exp2(fmaf(x, kLog2e, -mscaled));
           lsum += p;
           v[i] = p;
         }
@@ -274,7 +282,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_ld32(tmem_base + Cfg::kOffO + lane_off + uint32_t(c * 32), v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += v[i];
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, v[i]);
     }
     if (tq < T) {
       const float inv = 1.f / l;

@@ -188,6 +188,18 @@ def test_evaluator_matches_reference_eval_loop(ops):
     with torch.no_grad():
         res2 = ev.step(host_inputs=True)
     assert torch.equal(res2["scores"], res["scores"])
+    # ragged pinned-host path (raw [T_v, D] features, process_split on the device): the same bits again
+    ev.set_host_ragged(fi, fe)
+    with torch.no_grad():
+        res3 = ev.step(host_inputs=True)
+    assert torch.equal(res3["scores"], res["scores"]) and res3["AUC"] == res["AUC"] and res3["AP"] == res["AP"]
+    # ... and so does the full-rows path (every stage on the pad rows too)
+    ev.valid_rows_only = False
+    ev.set_device_features(ev.chunk_features(fi), ev.chunk_features(fe))
+    with torch.no_grad():
+        res4 = ev.step()
+    assert torch.equal(res4["scores"], res["scores"])
+    ev.valid_rows_only = True
     # class-wise and Ano-AUC against the oracle on our scores
     st = 0
     by, gby = {}, {}
