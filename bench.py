@@ -470,14 +470,16 @@ def main():
             traffic = json.load(fh).get("gemm_refine_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256, ROWMAJOR, *, CG2>: refinement Linears (tcgen05 bf16, fp32 accumulate)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256, ROWMAJOR, *, CG2>: refinement Linears (tcgen05 kind::f16, "
+                          + ("fp16" if str(model.temporal.precision) == "H" else "bf16") + " operands, fp32 accumulate)",
                 "achieved": round(ref_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": round(ref_tflops / peak_tf, 4), "traffic": traffic,
                 "launches": ref_n, "ms_per_launch": round(ref_ms / max(ref_n, 1), 5),
                 "peak_source": f"{pk['source']} sustained bf16 (MEASURED_PEAKS.json)",
-                "note": "algorithmic FLOPs (2*M*768*768 per launch; the 3-term bf16 split of plan B issues 3x the MMAs, "
-                        "not counted) / mean CUDA-event duration of the refinement GEMM launches of one step; traffic = "
-                        "dram bytes per launch from the ncu --set full capture in profiles/ (null until captured)",
+                "note": "algorithmic FLOPs (2*M*768*768 per launch, M = rows after the valid-row gather; the 3-term bf16 "
+                        "split of plan B issues 3x the MMAs, not counted) / mean CUDA-event duration of the refinement "
+                        "GEMM launches of one step; traffic = dram bytes per launch from the ncu --set full capture "
+                        "summarised in profiles/ (Linear2 is HBM-bound: fp32 residual in + fp32 / fp16 out)",
                 "share_of_step": round(ref_ms / max(sum(ms_k[:13]), 1e-9), 4),
                 "all_gemms": {"achieved": round(gemm_tflops, 2), "frac": round(gemm_tflops / peak_tf, 4),
                               "share_of_step": round(gemm_ms / max(sum(ms_k[:13]), 1e-9), 4)}}

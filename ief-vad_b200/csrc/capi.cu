@@ -23,7 +23,7 @@ using namespace iefvad;
 struct iefvad_model {
   Model impl;
   // scratch of the host-input forward: ping-pong input buffers filled on a copy stream while the previous part computes
-  DevBuf host_in[2][2], host_out[7], host_logits, host_scores;
+  DevBuf host_in[2][2], host_out[5], host_logits, host_scores;   // host_out: fused, mu x2, logvar x2 (scratch)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_start = nullptr;
   int64_t host_part_rows = 32768;
@@ -214,10 +214,10 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
     }
     IEF_CUDA(cudaEventRecord(m->ev_copied[buf], cs));
     IEF_CUDA(cudaStreamWaitEvent(st, m->ev_copied[buf], 0));
-    float* o[7];
-    for (int i = 0; i < 7; ++i) o[i] = m->host_out[i].as<float>();
+    float* o[5];
+    for (int i = 0; i < 5; ++i) o[i] = m->host_out[i].as<float>();
     IEF_TRY(m->impl.forward(m->host_in[buf][0].p, m->host_in[buf][1].p, in_dtype, Bs, T, o[0], ldev + o0, o[1], o[2], o[3],
-                            o[4], o[5], o[6], sdev ? sdev + o0 : nullptr, st, valid_len_host ? &vr : nullptr));
+                            o[4], nullptr, nullptr, sdev ? sdev + o0 : nullptr, st, valid_len_host ? &vr : nullptr));
     j0 += nvalid;
     IEF_CUDA(cudaEventRecord(m->ev_consumed[buf], st));
     if (logits_host) IEF_CUDA(cudaMemcpyAsync(logits_host + r0, ldev + r0, nr * 4, cudaMemcpyDeviceToHost, st));
@@ -272,9 +272,9 @@ int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev
     vr.rowmap = rowmap;
   }
   for (auto& b : m->host_out) IEF_TRY(b.reserve((rows ? rows : 1) * m->impl.D * 4));
-  float* o[7];
-  for (int i = 0; i < 7; ++i) o[i] = m->host_out[i].as<float>();
-  return m->impl.forward(img, ev, in_dtype, B, T, o[0], logits, o[1], o[2], o[3], o[4], o[5], o[6], scores, st,
+  float* o[5];
+  for (int i = 0; i < 5; ++i) o[i] = m->host_out[i].as<float>();
+  return m->impl.forward(img, ev, in_dtype, B, T, o[0], logits, o[1], o[2], o[3], o[4], nullptr, nullptr, scores, st,
                          valid_len_host ? &vr : nullptr);
 }
 

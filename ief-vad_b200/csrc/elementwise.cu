@@ -195,8 +195,10 @@ fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, co
       we[e] = __fdiv_rn(re, den);
       f[e] = __fadd_rn(__fmul_rn(wi[e], mi[e]), __fmul_rn(we[e], me[e]));
     }
-    __stcs(w_i + i, make_float4(wi[0], wi[1], wi[2], wi[3]));
-    __stcs(w_e + i, make_float4(we[0], we[1], we[2], we[3]));
+    if (w_i) {                                  // the evaluation forward does not return the fusion weights
+      __stcs(w_i + i, make_float4(wi[0], wi[1], wi[2], wi[3]));
+      __stcs(w_e + i, make_float4(we[0], we[1], we[2], we[3]));
+    }
     if (fused) fused[i] = make_float4(f[0], f[1], f[2], f[3]);
     if (fused_hi && hi_fp16) {                 // fp16 operand copy (refinement chain of plan H)
       const __half2 h01 = __floats2half2_rn(f[0], f[1]), h23 = __floats2half2_rn(f[2], f[3]);

@@ -249,8 +249,9 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
   IEF_TRY(check_loaded());
   IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
   if (B == 0 || T == 0) return IEFVAD_OK;
-  IEF_CHECK(img && ev && fused && logits && image_mu && event_mu && image_logvar && event_logvar && w_i && w_e,
+  IEF_CHECK(img && ev && fused && logits && image_mu && event_mu && image_logvar && event_logvar,
             "forward: null tensor pointer");
+  IEF_CHECK((w_i == nullptr) == (w_e == nullptr), "forward: w_i and w_e are written together or not at all");
   IEF_CHECK(T <= (1 << 24), "T=%lld too long", T);
   const bool fp32_plan = plan < 0;
   if (vr) {
@@ -383,7 +384,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     float* fused_out = fused + out0 * D;
     float* xcur = (R == 0) ? fused_out : x32.as<float>();
     IEF_PROF(KC_FUSE, double(Mo) * D * 28, fuse(image_mu + out0 * D, event_mu + out0 * D, image_logvar + out0 * D, event_logvar + out0 * D, Mo * D,
-                 factor, eps, w_i + out0 * D, w_e + out0 * D, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
+                 factor, eps, w_i ? w_i + out0 * D : nullptr, w_e ? w_e + out0 * D : nullptr, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
                  (rsp && R > 0) ? a_lo.as<bf16>() : nullptr, num_sms, stream, r16 ? 1 : 0));
     // iterative refinement (:146-149): x <- x - lambda * (W2 relu(W1 x + b1) + b2)
     for (int i = 0; i < R; ++i) {
