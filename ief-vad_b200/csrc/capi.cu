@@ -2,6 +2,7 @@
 #include "../../include/iefvad.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -27,6 +28,7 @@ struct iefvad_model {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_start = nullptr;
   int64_t host_part_rows = 32768;
+  uint64_t host_seq = 0;          // parts issued so far: the ping-pong of the input buffers continues across calls
 };
 
 namespace {
@@ -98,7 +100,7 @@ int iefvad_model_set_param(iefvad_model* m, const char* key, const float* data, 
 
 int iefvad_model_set_plan(iefvad_model* m, int plan) {
   IEF_CHECK(m, "null model");
-  IEF_CHECK(plan == IEFVAD_PLAN_FP32 || (plan >= 0 && plan <= 31), "unknown precision plan %d", plan);
+  IEF_CHECK(plan == IEFVAD_PLAN_FP32 || (plan >= 0 && plan <= 63), "unknown precision plan %d", plan);
   m->impl.plan = plan;
   return IEFVAD_OK;
 }
@@ -142,8 +144,17 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
     static const double env_first = [] { const char* e = getenv("IEFVAD_HOST_PART_FIRST"); return e ? atof(e) : 0.0; }();
     static const double env_growth = [] { const char* e = getenv("IEFVAD_HOST_PART_GROWTH"); return e ? atof(e) : 0.0; }();
     const bool ragged_in = chunk_start_dev != nullptr;
-    const double growth = env_growth > 1.0 ? env_growth : (ragged_in ? 3.0 : 1.4);
+    double growth = env_growth > 1.0 ? env_growth : (ragged_in ? 3.0 : 1.4);
     double want = env_first > 0.0 ? env_first : double(m->host_part_rows) / (ragged_in ? 8.0 : 4.0);
+    // Back-to-back calls: the previous call's last part is still computing, so this call's first copy hides behind
+    // it whatever its size - two halves then keep the GEMM grids full (a small first part only pays when the device
+    // is idle at the call).
+    if (env_first <= 0.0 && m->host_seq > 0 && m->ev_consumed[(m->host_seq - 1) & 1] &&
+        cudaEventQuery(m->ev_consumed[(m->host_seq - 1) & 1]) == cudaErrorNotReady) {
+      (void)cudaGetLastError();            // cudaErrorNotReady is a status, not a failure: keep it out of the next check
+      want = double(((B + 1) / 2) * T);
+      growth = 1.0;
+    }
     int64_t left = B;
     while (left > 0) {
       int64_t pb = int64_t(want / double(T));
@@ -154,6 +165,14 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
       partsB.push_back(pb);
       left -= pb;
       want *= growth;
+    }
+  }
+  {
+    static const bool debug = getenv("IEFVAD_HOST_DEBUG") != nullptr;      // print the part schedule of every call
+    if (debug) {
+      fprintf(stderr, "[iefvad] host forward %lld x %lld rows, parts:", (long long)B, (long long)T);
+      for (int64_t pb : partsB) fprintf(stderr, " %lld", (long long)(pb * T));
+      fprintf(stderr, "\n");
     }
   }
   int64_t maxB = 0;
@@ -180,13 +199,13 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
   float* ldev = logits_dev ? logits_dev : m->host_logits.as<float>();
   float* sdev = scores_dev ? scores_dev : (scores_host ? m->host_scores.as<float>() : nullptr);
   cudaStream_t cs = m->copy_stream;
-  // the copy stream must not run ahead of work already queued on the caller's stream that still reads the buffers
-  IEF_CUDA(cudaEventRecord(m->ev_start, st));
-  IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_start, 0));
+  // The copy stream only waits for the last forward that READ the buffer it is about to overwrite (ev_consumed, which
+  // persists across calls) - not for everything queued on the caller's stream - so in a loop of calls the first
+  // part of call k+1 already travels while call k is still computing its last part (and the caller's metrics).
   int64_t b0 = 0;
   size_t j0 = 0;                       // compact output offset (valid-rows mode)
   for (int p = 0; p < int(partsB.size()); b0 += partsB[p], ++p) {
-    const int buf = p & 1;
+    const int buf = int(m->host_seq++ & 1);
     const int64_t Bs = partsB[p];
     const size_t r0 = size_t(b0) * T, nr = size_t(Bs) * T;
     ValidRows vr;
@@ -198,7 +217,7 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
       vr.row_base = static_cast<long long>(r0);
     }
     const size_t o0 = valid_len_host ? j0 : r0;
-    if (p >= 2) IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_consumed[buf], 0));
+    IEF_CUDA(cudaStreamWaitEvent(cs, m->ev_consumed[buf], 0));      // no-op until the event has been recorded once
     // ragged: the host buffers hold only the valid rows, chunk after chunk - this part's rows are [j0, j0 + nvalid)
     const size_t src0 = ragged ? j0 : r0, nsrc = ragged ? nvalid : nr;
     if (ragged) {

@@ -130,7 +130,7 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
     wants.push_back({buf, D, false, &whiten_b[m], nullptr, nullptr});
     heads[m].out = 2 * D; heads[m].in = D;
     // mu and logvar of one modality share their input: stored as one [2D, D] matrix (rows [0,D) = mu)
-    wants.push_back({std::string("@heads_w.") + mods[m], 2LL * D * D, true, &heads[m].w, &heads[m].w_hi, &heads[m].w_lo});
+    wants.push_back({std::string("@heads_w.") + mods[m], 2LL * D * D, true, &heads[m].w, &heads[m].w_hi, &heads[m].w_lo, &heads[m].w_h16});
     wants.push_back({std::string("@heads_b.") + mods[m], 2LL * D, false, &heads[m].b, nullptr, nullptr});
   }
   for (int i = 0; i < R; ++i) {
@@ -188,6 +188,7 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
       ParamSlot sw;
       sw.dst = hw.dst + (long long)k * D * D; sw.numel = 1LL * D * D;
       sw.hi = hw.hi + (long long)k * D * D;   sw.lo = hw.lo + (long long)k * D * D;
+      sw.h16 = hw.h16 + (long long)k * D * D;
       snprintf(buf, sizeof(buf), "temporal.%s_%s.weight", mods[m], kinds[k]);
       slots[buf] = sw;
       ParamSlot sb;
@@ -348,10 +349,11 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
             g2.fp16 = a16;
             IEF_PROF(KC_GEMM_OUT, 2.0 * Mc * D * D, gemm_tc(g2, e2, num_sms, stream));
             // LN_i (+ whitening LN after the last layer, :117/:123); bf16 hi(/lo) feed the next GEMM
-            const bool need_lo = last ? (plan & PLAN_SPLIT_HEADS) != 0 : sp;
+            const bool h16 = (plan & PLAN_FP16_HEADS) != 0;                       // heads take fp16 operands, one pass
+            const bool need_lo = last ? (!h16 && (plan & PLAN_SPLIT_HEADS) != 0) : sp;
             IEF_PROF(KC_LAYERNORM, double(Mc) * D * 8, layernorm(yout, Mc, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
                               last ? whiten_b[m] : nullptr, 1e-5f, last ? nullptr : x32.as<float>(), a_hi.as<bf16>(),
-                              need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream, (a16 && !last) ? 1 : 0));
+                              need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream, ((a16 && !last) || (h16 && last)) ? 1 : 0));
           }
         }
       }
@@ -359,7 +361,8 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
         // no attention layers: only the whitening LN (model/imf_vad.py:117)
         IEF_PROF(KC_LAYERNORM, double(M) * D * 8, layernorm(x32.as<float>(), M, D, whiten_w[m], whiten_b[m], nullptr, nullptr, 1e-5f,
                           fp32_plan ? y32.as<float>() : nullptr, fp32_plan ? nullptr : a_hi.as<bf16>(),
-                          (!fp32_plan && (plan & PLAN_SPLIT_HEADS)) ? a_lo.as<bf16>() : nullptr, num_sms, stream));
+                          (!fp32_plan && (plan & PLAN_SPLIT_HEADS) && !(plan & PLAN_FP16_HEADS)) ? a_lo.as<bf16>() : nullptr,
+                          num_sms, stream, (!fp32_plan && (plan & PLAN_FP16_HEADS)) ? 1 : 0));
         if (fp32_plan) IEF_CUDA(cudaMemcpyAsync(x32.p, y32.p, size_t(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
       }
       // heads (:125-128): one [M, D] x [2D, D]^T GEMM per modality, mu and logvar written to the user tensors
@@ -371,9 +374,11 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
         IEF_PROF(KC_GEMM_SIMT, 4.0 * Mo * D * D, gemm_simt(x32.as<float>(), D, heads[m].w, D, int(Mo), 2 * D, D, eh, stream));
       } else {
         GemmTcArgs gh;
-        gh.A_hi = a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>(); gh.W_hi = heads[m].w_hi; gh.W_lo = heads[m].w_lo;
+        const bool h16 = (plan & PLAN_FP16_HEADS) != 0;
+        gh.A_hi = a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>(); gh.W_hi = h16 ? heads[m].w_h16 : heads[m].w_hi; gh.W_lo = heads[m].w_lo;
         gh.M = int(Mo); gh.N = 2 * D; gh.K = D; gh.lda = D; gh.ldw = D;
-        gh.nsplit = (plan & PLAN_SPLIT_HEADS) ? 3 : 1;
+        gh.nsplit = (!h16 && (plan & PLAN_SPLIT_HEADS)) ? 3 : 1;
+        gh.fp16 = h16 ? 1 : 0;
         IEF_PROF(KC_GEMM_HEADS, 4.0 * Mo * D * D, gemm_tc(gh, eh, num_sms, stream));
       }
     }

@@ -20,7 +20,7 @@ namespace iefvad {
 // operands - fp16 inputs are then exact, and the attention core is where bf16's mantissa dominates the error once the
 // heads / refinement are taken care of (zero-padded clips: 1.4e-3 with bf16, 1.7e-4 with fp16)
 enum : int { PLAN_FP32 = -1, PLAN_SPLIT_ENCODER = 1, PLAN_SPLIT_HEADS = 2, PLAN_SPLIT_REFINE = 4, PLAN_FP16_REFINE = 8,
-             PLAN_FP16_ATTENTION = 16 };
+             PLAN_FP16_ATTENTION = 16, PLAN_FP16_HEADS = 32 };
 
 struct DevBuf {
   void* p = nullptr;
@@ -69,7 +69,7 @@ struct ValidRows {
 struct Model {
   int D = 0, H = 0, L = 0, R = 0, dh = 0, dhp = 0;
   float lambda_ref = 0.5f, factor = 1.f, eps = 1e-8f;
-  int plan = PLAN_SPLIT_HEADS | PLAN_FP16_REFINE | PLAN_FP16_ATTENTION;
+  int plan = PLAN_FP16_HEADS | PLAN_FP16_REFINE | PLAN_FP16_ATTENTION;
   long long max_rows = 262144;   // rows per internal slab (whole batch elements); ~18 KB of workspace per row
   int num_sms = 148;
   int device = 0;

@@ -35,7 +35,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         self.nu = nu
         self.epsilon = epsilon
         self.dropout = dropout          # attention dropout only acts in train(); this path is forward-only (eval)
-        self.precision = os.environ.get("IEFVAD_PLAN", "H")
+        self.precision = os.environ.get("IEFVAD_PLAN", "HH")
 
         # nn.MultiheadAttention / LayerNorm / Linear instances are used purely as parameter containers: they give
         # the reference's state_dict keys and consume the RNG exactly like the reference constructor does

@@ -45,6 +45,8 @@ extern "C" {
 #define IEFVAD_PLAN_B (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_SPLIT_REFINE) /* bf16 operands everywhere */
 #define IEFVAD_PLAN_FP16_ATTENTION 16 /* encoder (QKV in-projection, attention core, out-projection): fp16 operands */
 #define IEFVAD_PLAN_H (IEFVAD_PLAN_SPLIT_HEADS | IEFVAD_PLAN_FP16_REFINE | IEFVAD_PLAN_FP16_ATTENTION)
+#define IEFVAD_PLAN_FP16_HEADS 32 /* mu / logvar heads: fp16 operands, one MMA pass (overrides SPLIT_HEADS) */
+#define IEFVAD_PLAN_HH (IEFVAD_PLAN_FP16_HEADS | IEFVAD_PLAN_FP16_REFINE | IEFVAD_PLAN_FP16_ATTENTION) /* fp16 operands everywhere */
 /* ^ default: fp16 (11-bit mantissa, same tcgen05 kind::f16 rate) where bf16's 8-bit mantissa limits accuracy */
 
 int iefvad_abi_version(void);
