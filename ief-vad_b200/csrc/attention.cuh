@@ -19,6 +19,11 @@ struct AttnTcArgs {
 
 int attn_tc(const AttnTcArgs& a, cudaStream_t stream);
 
+// T <= 256 without masks (every chunk the reference's callers produce): persistent kernel, P kept in TMEM
+// (attention_short.cu).  attn_tc dispatches here when attn_short_supported(a); IEFVAD_ATTN_SHORT=0 disables it.
+bool attn_short_supported(const AttnTcArgs& a);
+int attn_short(const AttnTcArgs& a, cudaStream_t stream);
+
 // fp32 plan: qkv fp32 [B*T, 3*H*dh] (bias added, q unscaled) -> out fp32 [B*T, H*dh]
 int attn_simt(const float* qkv, float* out, int B, int T, int H, int dh, const float* attn_mask,
               const uint8_t* key_pad, cudaStream_t stream);

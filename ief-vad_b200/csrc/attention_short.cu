@@ -1,0 +1,355 @@
+// Self-attention core for SHORT sequences (T <= 256, no masks) - the shape every reference caller produces: test-time
+// videos are cut into 256-row chunks (data/tools.py:100-114), training clips are pooled / padded to 256
+// (data/tools.py:89-97), and nn.MultiheadAttention attends over all rows of the chunk (model/imf_vad.py:115,121).
+//
+// Persistent kernel, one CTA per SM, work item = one (batch element, head): both 128-row query tiles share one copy of
+// K and V^T in shared memory.  The whole key range fits one MMA (N = 256), so there is no online softmax:
+//   S_t = Q_t.K^T (128 x 256 fp32) lands in the 256 TMEM columns of tile t,
+//   16 softmax warps (two threads per query row, 128 keys each) take the exact row max, write P = exp(S - max) as
+//   packed 16-bit pairs back INTO TMEM over the S columns they have already consumed,
+//   O_t = P_t.V runs with the A operand read from TMEM (tcgen05.mma [d], [a], b-desc) into free columns of the tile,
+//   the same threads normalise and store their half row.
+// Nothing of P ever touches shared memory; Q / K / V^T buffers are released by tcgen05.commit as soon as their last
+// MMA retires, so the next item's TMA loads overlap this item's softmax.  TMEM columns of tile t (base 256 t):
+//   [0, 64) P keys 0..127 | [64, 64 + DH) O | [192, 256) P keys 128..255    (all inside the dead S columns).
+#include <cstdlib>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "tensormap.cuh"
+
+namespace iefvad {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kSoftmaxWarps = 16;
+constexpr int kThreads = (kSoftmaxWarps + 2) * 32;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x K 16-bit elements, two per 32-bit column
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int DH, int DHP>
+struct ShortCfg {
+  static constexpr int TK = 256;                                   // keys covered by one S MMA
+  static constexpr uint32_t kQChunk = 128 * 128;                   // [128 rows x 64 columns] 128B-swizzled
+  static constexpr uint32_t kQTile = (DHP / 64) * kQChunk;
+  static constexpr uint32_t kKChunk = TK * 128;
+  static constexpr uint32_t kKBytes = (DHP / 64) * kKChunk;
+  static constexpr uint32_t kVSub = DH * 128;                      // [DH rows x 64 keys]
+  static constexpr uint32_t kVBytes = (TK / 64) * kVSub;
+  static constexpr uint32_t kOffK = 2 * kQTile;
+  static constexpr uint32_t kOffV = kOffK + kKBytes;
+  static constexpr uint32_t kOffX = kOffV + kVBytes;               // row max / row sum exchange between the two halves
+  static constexpr uint32_t kXBytes = 2 * 2 * 2 * 2 * 128 * 4;     // {max, sum} x parity x tile x half x row
+  static constexpr uint32_t kOffBar = kOffX + kXBytes;
+  static constexpr size_t kSmemBytes = 1024 + kOffBar + 256;
+  static constexpr uint32_t kColP0 = 0, kColO = 64, kColP1 = 192;
+  static_assert(kColO + DH <= kColP1, "O does not fit between the two P halves");
+  static_assert(DH % 32 == 0, "each thread stores DH / 2 columns in 16-column pieces");
+};
+
+template <int DH, int DHP>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H, int n_items,
+                  int fp16, int out_fp16) {
+  using Cfg = ShortCfg<DH, DHP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* qk_empty = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* v_empty = bars + 3;
+  uint64_t* s_full = bars + 4;    // [2]
+  uint64_t* s_empty = bars + 6;   // [2]
+  uint64_t* p_full = bars + 8;    // [2]
+  uint64_t* o_full = bars + 10;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::kOffX);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kSoftmaxWarps && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmVt);
+    mbar_init(qk_full, 1);
+    mbar_init(qk_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_empty[t], 256);
+      mbar_init(&p_full[t], 256);
+      mbar_init(&o_full[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kSoftmaxWarps + 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kSoftmaxWarps) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(qk_empty, ph ^ 1);
+        mbar_arrive_expect_tx(qk_full, 2 * Cfg::kQTile + Cfg::kKBytes);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int c = 0; c < DHP / 64; ++c)
+            tma_load_3d(&tmQ, qk_full, smem + t * Cfg::kQTile + c * Cfg::kQChunk, c * 64, t * 128, item);
+#pragma unroll
+        for (int c = 0; c < DHP / 64; ++c)
+          tma_load_3d(&tmK, qk_full, smem + Cfg::kOffK + c * Cfg::kKChunk, c * 64, 0, item);
+        mbar_wait(v_empty, ph ^ 1);
+        mbar_arrive_expect_tx(v_full, Cfg::kVBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::TK / 64; ++c)
+          tma_load_3d(&tmVt, v_full, smem + Cfg::kOffV + c * Cfg::kVSub, c * 64, 0, item);
+      }
+    }
+  } else if (warp == kSoftmaxWarps + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = fp16 ? make_idesc_f16(128, Cfg::TK) : make_idesc_bf16(128, Cfg::TK);
+      const uint32_t idesc_o = fp16 ? make_idesc_f16(128, DH) : make_idesc_bf16(128, DH);
+      const uint32_t sq = smem_u32(smem), sk = smem_u32(smem + Cfg::kOffK), sv = smem_u32(smem + Cfg::kOffV);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(qk_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&s_empty[t], ph ^ 1);       // tile t's columns (P and O of the previous item) have been read out
+          tc_fence_after();
+          const uint32_t d = tmem_base + uint32_t(t * 256);
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {   // only the DH real columns of the DHP-padded rows
+            const int c = kk >> 2, k4 = kk & 3;
+            umma_bf16(d, make_smem_desc_sw128(sq + t * Cfg::kQTile + c * Cfg::kQChunk) + uint64_t(2 * k4),
+                      make_smem_desc_sw128(sk + c * Cfg::kKChunk) + uint64_t(2 * k4), idesc_s, kk != 0 ? 1u : 0u);
+          }
+          tc_commit(&s_full[t]);
+        }
+        tc_commit(qk_empty);                     // Q and K may be overwritten once both S MMAs have retired
+        mbar_wait(v_full, ph);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], ph);
+          tc_fence_after();
+          const uint32_t tb = tmem_base + uint32_t(t * 256);
+#pragma unroll
+          for (int kk = 0; kk < Cfg::TK / 16; ++kk) {
+            const int c = kk >> 2, k4 = kk & 3;
+            const uint32_t a = tb + (kk < 8 ? Cfg::kColP0 + uint32_t(kk * 8) : Cfg::kColP1 + uint32_t((kk - 8) * 8));
+            umma_f16_ts(tb + Cfg::kColO, a, make_smem_desc_sw128(sv + c * Cfg::kVSub) + uint64_t(2 * k4), idesc_o,
+                        kk != 0 ? 1u : 0u);
+          }
+          tc_commit(&o_full[t]);
+        }
+        tc_commit(v_empty);
+      }
+    }
+  } else {
+    // ===================== softmax / normalise / store (warps 0..15) =====================
+    const int t = warp >> 3;                        // query tile
+    const int hf = (warp >> 2) & 1;                 // key half: keys [128 hf, 128 hf + 128)
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;              // query row inside the tile == TMEM lane
+    const int tq = t * 128 + r;
+    const uint32_t tbase = tmem_base + uint32_t(t * 256) + (uint32_t(quarter * 32) << 16);
+    const uint32_t ts = tbase + uint32_t(hf * 128);
+    const uint32_t tp = tbase + (hf ? Cfg::kColP1 : Cfg::kColP0);
+    const int key0 = hf * 128;
+    const bool tail = T < Cfg::TK;
+    // exchange slots: xch[((kind * 2 + parity) * 2 + tile) * 2 + half][row]
+    auto slot = [&](int kind, uint32_t ph, int half) { return xch + ((((kind * 2 + int(ph)) * 2 + t) * 2 + half) << 7) + r; };
+
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int b = item / H, h = item - b * H;
+      mbar_wait(&s_full[t], ph);
+      tc_fence_after();
+      // ---- pass 1: row max over this thread's 128 keys
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        float v0[32], v1[32];
+        tmem_ld32(ts + uint32_t(c2 * 64), v0);
+        tmem_ld32(ts + uint32_t(c2 * 64 + 32), v1);
+        tmem_ld_wait();
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (key0 + c2 * 64 + i < T) mx = fmaxf(mx, v0[i]);
+            if (key0 + c2 * 64 + 32 + i < T) mx = fmaxf(mx, v1[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(v0[i], v1[i]));
+        }
+      }
+      *slot(0, ph, hf) = mx;
+      named_bar_sync(1 + t, 256);
+      mx = fmaxf(mx, *slot(0, ph, hf ^ 1));          // key 0 is always valid, so the row max is finite
+      const float mscaled = mx * kLog2e;
+      // ---- pass 2: P = exp(S - max) -> packed 16-bit pairs over the S columns already consumed.  Half 0 walks its
+      // chunks upwards and packs downwards into [0, 64); half 1 walks downwards and packs into [192, 256).
+      float lsum = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = hf ? 3 - ci : ci;
+        float v[32];
+        tmem_ld32(ts + uint32_t(c * 32), v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = fast_exp2(fmaf(v[i], kLog2e, -mscaled));
+          float p1 = fast_exp2(fmaf(v[i + 1], kLog2e, -mscaled));
+          if (tail) {
+            if (key0 + c * 32 + i >= T) p0 = 0.f;
+            if (key0 + c * 32 + i + 1 >= T) p1 = 0.f;
+          }
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_16x2(p0, p1, fp16);
+        }
+        tmem_st16(tp + uint32_t(c * 16), pk);
+      }
+      *slot(1, ph, hf) = lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+      // ---- O = P.V: this thread normalises and stores columns [hf DH/2, hf DH/2 + DH/2) of its row
+      mbar_wait(&o_full[t], ph);
+      tc_fence_after();
+      named_bar_sync(1 + t, 256);
+      const float inv = 1.f / (lsum + *slot(1, ph, hf ^ 1));
+      float o[DH / 2];
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) tmem_ld16(tbase + Cfg::kColO + uint32_t(hf * (DH / 2) + c * 16), o + c * 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[t]);
+      if (tq < T) {
+        bf16* dst = out + ((long long)b * T + tq) * ldo + h * DH + hf * (DH / 2);
+#pragma unroll
+        for (int d = 0; d < DH / 2; d += 8) {
+          uint4 u;
+          u.x = pack_16x2(o[d + 0] * inv, o[d + 1] * inv, out_fp16);
+          u.y = pack_16x2(o[d + 2] * inv, o[d + 3] * inv, out_fp16);
+          u.z = pack_16x2(o[d + 4] * inv, o[d + 5] * inv, out_fp16);
+          u.w = pack_16x2(o[d + 6] * inv, o[d + 7] * inv, out_fp16);
+          *reinterpret_cast<uint4*>(dst + d) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kSoftmaxWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int DH, int DHP>
+int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
+  using Cfg = ShortCfg<DH, DHP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IEF_CUDA(cudaFuncSetAttribute(attn_short_kernel<DH, DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(Cfg::kSmemBytes)));
+    attr_set = true;
+  }
+  const uint64_t BH = uint64_t(a.B) * a.H;
+  CUtensorMap tq, tk, tv;
+  IEF_TRY(make_tmap_3d(&tq, a.q, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, 128, 1));
+  IEF_TRY(make_tmap_3d(&tk, a.k, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, Cfg::TK, 1));
+  IEF_TRY(make_tmap_3d(&tv, a.vt, a.T, DH, BH, uint64_t(a.Tpad) * 2, uint64_t(DH) * a.Tpad * 2, 64, DH, 1));
+  const int n_items = int(BH);
+  const int grid = n_items < num_sms ? n_items : num_sms;
+  attn_short_kernel<DH, DHP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, n_items,
+                                                                         a.fp16, a.out_fp16);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+}  // namespace
+
+bool attn_short_supported(const AttnTcArgs& a) {
+  static const int env_off = [] { const char* e = getenv("IEFVAD_ATTN_SHORT"); return (e && atoi(e) == 0) ? 1 : 0; }();
+  return !env_off && a.T <= 256 && !a.attn_mask && !a.key_pad && uint64_t(a.B) * a.H < (1ull << 31);
+}
+
+int attn_short(const AttnTcArgs& a, cudaStream_t stream) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    IEF_CUDA(cudaGetDevice(&dev));
+    IEF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+#define IEF_ATTN_SHORT(DH_, DHP_) \
+  if (a.dh == DH_ && a.dhp == DHP_) return launch_attn_short<DH_, DHP_>(a, num_sms, stream);
+  IEF_ATTN_SHORT(96, 128)
+  IEF_ATTN_SHORT(64, 64)
+  IEF_ATTN_SHORT(128, 128)
+  IEF_ATTN_SHORT(32, 64)
+#undef IEF_ATTN_SHORT
+  set_error("attn_short: unsupported head dim %d (padded %d); supported: 32, 64, 96, 128", a.dh, a.dhp);
+  return IEFVAD_ERR_INVALID;
+}
+
+}  // namespace iefvad
