@@ -12,6 +12,7 @@
 // Nothing of P ever touches shared memory; Q / K / V^T buffers are released by tcgen05.commit as soon as their last
 // MMA retires, so the next item's TMA loads overlap this item's softmax.  TMEM columns of tile t (base 256 t):
 //   [0, 64) P keys 0..127 | [64, 64 + DH) O | [192, 256) P keys 128..255    (all inside the dead S columns).
+#include <cstdio>
 #include <cstdlib>
 
 #include "attention.cuh"
@@ -90,8 +91,10 @@ template <int DH, int DHP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H, int n_items,
-                  int fp16, int out_fp16) {
+                  int fp16, int out_fp16, long long* __restrict__ trace) {
   using Cfg = ShortCfg<DH, DHP>;
+  // debug timeline (IEFVAD_ATTN_TRACE): CTA 0 records clock64() of pipeline events, 16 slots per item
+  auto mark = [&](int it, int ev) { if (trace && blockIdx.x == 0 && it < 64) trace[it * 16 + ev] = clock64(); };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
@@ -140,6 +143,7 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
         mbar_wait(qk_empty, ph ^ 1);
+        mark(it, 0);
         mbar_arrive_expect_tx(qk_full, 2 * Cfg::kQTile + Cfg::kKBytes);
 #pragma unroll
         for (int t = 0; t < 2; ++t)
@@ -149,7 +153,21 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int c = 0; c < DHP / 64; ++c)
           tma_load_3d(&tmK, qk_full, smem + Cfg::kOffK + c * Cfg::kKChunk, c * 64, 0, item);
+        // the next item starts streaming from HBM into L2 now: its shared-memory loads (issued when the S / P.V
+        // MMAs of this item have retired) then only pay the L2 latency
+        if (item + int(gridDim.x) < n_items) {
+          const int nx = item + int(gridDim.x);
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < DHP / 64; ++c) tma_prefetch_3d(&tmQ, c * 64, t * 128, nx);
+#pragma unroll
+          for (int c = 0; c < DHP / 64; ++c) tma_prefetch_3d(&tmK, c * 64, 0, nx);
+#pragma unroll
+          for (int c = 0; c < Cfg::TK / 64; ++c) tma_prefetch_3d(&tmVt, c * 64, 0, nx);
+        }
         mbar_wait(v_empty, ph ^ 1);
+        mark(it, 1);
         mbar_arrive_expect_tx(v_full, Cfg::kVBytes);
 #pragma unroll
         for (int c = 0; c < Cfg::TK / 64; ++c)
@@ -162,41 +180,61 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t idesc_s = fp16 ? make_idesc_f16(128, Cfg::TK) : make_idesc_bf16(128, Cfg::TK);
       const uint32_t idesc_o = fp16 ? make_idesc_f16(128, DH) : make_idesc_bf16(128, DH);
       const uint32_t sq = smem_u32(smem), sk = smem_u32(smem + Cfg::kOffK), sv = smem_u32(smem + Cfg::kOffV);
+      auto issue_s = [&](int t) {
+        const uint32_t d = tmem_base + uint32_t(t * 256);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {   // only the DH real columns of the DHP-padded rows
+          const int c = kk >> 2, k4 = kk & 3;
+          umma_bf16(d, make_smem_desc_sw128(sq + t * Cfg::kQTile + c * Cfg::kQChunk) + uint64_t(2 * k4),
+                    make_smem_desc_sw128(sk + c * Cfg::kKChunk) + uint64_t(2 * k4), idesc_s, kk != 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t) {
+        const uint32_t tb = tmem_base + uint32_t(t * 256);
+#pragma unroll
+        for (int kk = 0; kk < Cfg::TK / 16; ++kk) {
+          const int c = kk >> 2, k4 = kk & 3;
+          const uint32_t a = tb + (kk < 8 ? Cfg::kColP0 + uint32_t(kk * 8) : Cfg::kColP1 + uint32_t((kk - 8) * 8));
+          umma_f16_ts(tb + Cfg::kColO, a, make_smem_desc_sw128(sv + c * Cfg::kVSub) + uint64_t(2 * k4), idesc_o,
+                      kk != 0 ? 1u : 0u);
+        }
+        tc_commit(&o_full[t]);
+      };
+      // The two query tiles run half an item apart: S_a(i), P.V_b(i-1), S_b(i), P.V_a(i).  While tile a's softmax
+      // owns the SFU, the tensor pipe serves tile b, and vice versa (in lock-step both would wait at the same time).
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
         mbar_wait(qk_full, ph);
+        mark(it, 2);
+        mbar_wait(&s_empty[0], ph ^ 1);         // tile 0's columns (P and O of the previous item) have been read out
+        mark(it, 3);
         tc_fence_after();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&s_empty[t], ph ^ 1);       // tile t's columns (P and O of the previous item) have been read out
+        issue_s(0);
+        if (it > 0) {
+          mbar_wait(&p_full[1], ph ^ 1);
+          mark(it - 1, 7);
           tc_fence_after();
-          const uint32_t d = tmem_base + uint32_t(t * 256);
-#pragma unroll
-          for (int kk = 0; kk < DH / 16; ++kk) {   // only the DH real columns of the DHP-padded rows
-            const int c = kk >> 2, k4 = kk & 3;
-            umma_bf16(d, make_smem_desc_sw128(sq + t * Cfg::kQTile + c * Cfg::kQChunk) + uint64_t(2 * k4),
-                      make_smem_desc_sw128(sk + c * Cfg::kKChunk) + uint64_t(2 * k4), idesc_s, kk != 0 ? 1u : 0u);
-          }
-          tc_commit(&s_full[t]);
+          issue_pv(1);                          // previous item, still on the previous V
+          tc_commit(v_empty);
         }
-        tc_commit(qk_empty);                     // Q and K may be overwritten once both S MMAs have retired
+        mbar_wait(&s_empty[1], ph ^ 1);
+        mark(it, 4);
+        tc_fence_after();
+        issue_s(1);
+        tc_commit(qk_empty);                    // Q and K may be overwritten once both S MMAs have retired
         mbar_wait(v_full, ph);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], ph);
-          tc_fence_after();
-          const uint32_t tb = tmem_base + uint32_t(t * 256);
-#pragma unroll
-          for (int kk = 0; kk < Cfg::TK / 16; ++kk) {
-            const int c = kk >> 2, k4 = kk & 3;
-            const uint32_t a = tb + (kk < 8 ? Cfg::kColP0 + uint32_t(kk * 8) : Cfg::kColP1 + uint32_t((kk - 8) * 8));
-            umma_f16_ts(tb + Cfg::kColO, a, make_smem_desc_sw128(sv + c * Cfg::kVSub) + uint64_t(2 * k4), idesc_o,
-                        kk != 0 ? 1u : 0u);
-          }
-          tc_commit(&o_full[t]);
-        }
-        tc_commit(v_empty);
+        mark(it, 5);
+        mbar_wait(&p_full[0], ph);
+        mark(it, 6);
+        tc_fence_after();
+        issue_pv(0);
+      }
+      if (it > 0) {
+        mbar_wait(&p_full[1], (it - 1) & 1);
+        tc_fence_after();
+        issue_pv(1);
       }
     }
   } else {
@@ -219,6 +257,7 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t ph = it & 1;
       const int b = item / H, h = item - b * H;
       mbar_wait(&s_full[t], ph);
+      if (threadIdx.x == 0 || threadIdx.x == 256) mark(it, 8 + t);
       tc_fence_after();
       // ---- pass 1: row max over this thread's 128 keys
       float mx = -INFINITY;
@@ -243,6 +282,7 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       named_bar_sync(1 + t, 256);
       mx = fmaxf(mx, *slot(0, ph, hf ^ 1));          // key 0 is always valid, so the row max is finite
       const float mscaled = mx * kLog2e;
+      if (threadIdx.x == 0) mark(it, 10);
       // ---- pass 2: P = exp(S - max) -> packed 16-bit pairs over the S columns already consumed.  Half 0 walks its
       // chunks upwards and packs downwards into [0, 64); half 1 walks downwards and packs into [192, 256).
       float lsum = 0.f;
@@ -270,8 +310,10 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      if (threadIdx.x == 0) mark(it, 11);
       // ---- O = P.V: this thread normalises and stores columns [hf DH/2, hf DH/2 + DH/2) of its row
       mbar_wait(&o_full[t], ph);
+      if (threadIdx.x == 0 || threadIdx.x == 256) mark(it, 12 + t);
       tc_fence_after();
       named_bar_sync(1 + t, 256);
       const float inv = 1.f / (lsum + *slot(1, ph, hf ^ 1));
@@ -281,6 +323,7 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[t]);
+      if (threadIdx.x == 0) mark(it, 14);
       if (tq < T) {
         bf16* dst = out + ((long long)b * T + tq) * ldo + h * DH + hf * (DH / 2);
 #pragma unroll
@@ -320,10 +363,28 @@ int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
   IEF_TRY(make_tmap_3d(&tv, a.vt, a.T, DH, BH, uint64_t(a.Tpad) * 2, uint64_t(DH) * a.Tpad * 2, 64, DH, 1));
   const int n_items = int(BH);
   const int grid = n_items < num_sms ? n_items : num_sms;
+  static const bool want_trace = getenv("IEFVAD_ATTN_TRACE") != nullptr;
+  static long long* trace = nullptr;
+  static int traced = 0;
+  if (want_trace && !trace) {
+    IEF_CUDA(cudaMallocManaged(&trace, 64 * 16 * sizeof(long long)));
+    for (int i = 0; i < 64 * 16; ++i) trace[i] = 0;
+  }
   attn_short_kernel<DH, DHP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, n_items,
-                                                                         a.fp16, a.out_fp16);
+                                                                         a.fp16, a.out_fp16, (want_trace && traced < 3) ? trace : nullptr);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
+  if (want_trace && traced < 3 && n_items >= 8 * grid) {
+    ++traced;
+    IEF_CUDA(cudaStreamSynchronize(stream));
+    // columns: 0 qk_empty seen (producer) 1 v_empty seen 2 qk_full seen (MMA) 3/4 s_empty[0/1] seen 5 v_full seen
+    // 6/7 p_full[0/1] seen 8/9 s_full[0/1] seen (softmax) 10 row max known 11 P written 12/13 o_full[0/1] seen 14 O read
+    for (int it = 2; it < 8; ++it) {
+      fprintf(stderr, "[attn_short trace] item %d:", it);
+      for (int e = 0; e < 15; ++e) fprintf(stderr, " %lld", trace[it * 16 + e] - trace[2 * 16 + 2]);
+      fprintf(stderr, "\n");
+    }
+  }
   return IEFVAD_OK;
 }
 
