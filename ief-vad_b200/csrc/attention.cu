@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(192, AttnCfg<DH, DHP, KB>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H,
                const float* __restrict__ attn_mask /* [T,T] additive or null */,
-               const uint8_t* __restrict__ key_pad /* [B,T] 1 = ignore, or null */, int fp16, int out_fp16) {
+               const uint8_t* __restrict__ key_pad /* [B,T] 1 = ignore, or null */, int fp16, int out_fp16,
+               const int* __restrict__ row_out) {
   using Cfg = AttnCfg<DH, DHP, KB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -284,9 +285,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, v[i]);
     }
-    if (tq < T) {
+    long long ro = (long long)b * T + (tq < T ? tq : 0);
+    if (row_out) ro = __ldg(row_out + ro);
+    if (tq < T && ro >= 0) {
       const float inv = 1.f / l;
-      bf16* dst = out + ((long long)b * T + tq) * ldo + h * DH;
+      bf16* dst = out + ro * ldo + h * DH;
 #pragma unroll
       for (int d = 0; d < DH; d += 8) {
         uint4 u;
@@ -323,7 +326,7 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
   IEF_TRY(make_tmap_3d(&tv, a.vt, a.T, DH, BH, uint64_t(a.Tpad) * 2, uint64_t(DH) * a.Tpad * 2, 64, DH, 1));
   dim3 grid((a.T + QB - 1) / QB, a.H, a.B);
   attn_tc_kernel<DH, DHP, KB><<<grid, 192, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, a.attn_mask,
-                                                                  a.key_pad, a.fp16, a.out_fp16);
+                                                                  a.key_pad, a.fp16, a.out_fp16, a.row_out);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

@@ -14,6 +14,7 @@ struct AttnTcArgs {
   const uint8_t* key_pad = nullptr;    // optional [B, T], non-zero = ignore key
   int fp16 = 0;                        // q / k / vt hold fp16 and P is rounded to fp16 (11-bit mantissa), else bf16
   int out_fp16 = 0;                    // `out` receives fp16 instead of bf16
+  const int* row_out = nullptr;        // optional [B*T]: output row of query row b*T+t (compact layouts), < 0 = drop
   int key_block = 0;                   // 0 = heuristic (64 keys per block up to T = 2048, else 128), or 64 / 128
 };
 

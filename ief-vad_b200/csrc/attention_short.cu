@@ -91,7 +91,7 @@ template <int DH, int DHP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H, int n_items,
-                  int fp16, int out_fp16, long long* __restrict__ trace) {
+                  int fp16, int out_fp16, const int* __restrict__ row_out, long long* __restrict__ trace) {
   using Cfg = ShortCfg<DH, DHP>;
   // debug timeline (IEFVAD_ATTN_TRACE): CTA 0 records clock64() of pipeline events, 16 slots per item
   auto mark = [&](int it, int ev) { if (trace && blockIdx.x == 0 && it < 64) trace[it * 16 + ev] = clock64(); };
@@ -324,8 +324,10 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       mbar_arrive(&s_empty[t]);
       if (threadIdx.x == 0) mark(it, 14);
-      if (tq < T) {
-        bf16* dst = out + ((long long)b * T + tq) * ldo + h * DH + hf * (DH / 2);
+      long long ro = (long long)b * T + tq;
+      if (tq < T && row_out) ro = __ldg(row_out + ro);
+      if (tq < T && ro >= 0) {
+        bf16* dst = out + ro * ldo + h * DH + hf * (DH / 2);
 #pragma unroll
         for (int d = 0; d < DH / 2; d += 8) {
           uint4 u;
@@ -371,7 +373,7 @@ int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
     for (int i = 0; i < 64 * 16; ++i) trace[i] = 0;
   }
   attn_short_kernel<DH, DHP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, n_items,
-                                                                         a.fp16, a.out_fp16, (want_trace && traced < 3) ? trace : nullptr);
+                                                                         a.fp16, a.out_fp16, a.row_out, (want_trace && traced < 3) ? trace : nullptr);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   if (want_trace && traced < 3 && n_items >= 8 * grid) {

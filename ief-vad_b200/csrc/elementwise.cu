@@ -116,7 +116,8 @@ template <int NV>   // D = 128 * NV
 __global__ void __launch_bounds__(kThreads)
 layernorm_kernel(const float* __restrict__ x, long long M, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, const float* __restrict__ b2, float eps, float* __restrict__ out_f32,
-                 bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int hi_fp16) {
+                 bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int hi_fp16,
+                 const int* __restrict__ f32_row_out) {
   constexpr int D = 128 * NV;
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -157,7 +158,13 @@ layernorm_kernel(const float* __restrict__ x, long long M, const float* __restri
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const long long off = row * D + (lane + 32 * i) * 4;
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (out_f32) {
+        // the fp32 copy may go to a compact row (or nowhere): only rows that survive the valid-row cut need it
+        const long long ro = f32_row_out ? (long long)__ldg(f32_row_out + row) : row;
+        if (ro >= 0)
+          *reinterpret_cast<float4*>(out_f32 + ro * D + (lane + 32 * i) * 4) =
+              make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
       if (out_hi && hi_fp16) {
         uint2 u;
         u.x = pack_16x2(v[4 * i], v[4 * i + 1], 1);
@@ -214,6 +221,12 @@ fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, co
       if (fused_lo) *reinterpret_cast<uint2*>(fused_lo + i * 4) = *reinterpret_cast<uint2*>(l);
     }
   }
+}
+
+__global__ void __launch_bounds__(kThreads)
+inverse_rowmap_kernel(const int* __restrict__ rowmap, long long row_base, long long n_rows, int* __restrict__ inv) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += (long long)gridDim.x * blockDim.x)
+    inv[(long long)rowmap[j] - row_base] = int(j);
 }
 
 // one warp per output row: 16-byte vectors, D % 8 == 0
@@ -322,14 +335,15 @@ int ingest_ragged(const void* packed, int dtype, const long long* chunk_start, l
 }
 
 int layernorm(const float* x, long long M, int D, const float* w1, const float* b1, const float* w2, const float* b2,
-              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream, int hi_fp16) {
+              float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream, int hi_fp16,
+              const int* f32_row_out) {
   IEF_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: D=%d must be a multiple of 128 in [128, 1024]", D);
   IEF_CHECK(w1 && b1 && (w2 == nullptr) == (b2 == nullptr), "layernorm: bad affine pointers");
   if (M == 0) return IEFVAD_OK;
   const int grid = grid_for(M * 32, num_sms);
 #define IEF_LN(NV)                                                                                              \
   case NV:                                                                                                      \
-    layernorm_kernel<NV><<<grid, kThreads, 0, stream>>>(x, M, w1, b1, w2, b2, eps, out_f32, out_hi, out_lo, hi_fp16);  \
+    layernorm_kernel<NV><<<grid, kThreads, 0, stream>>>(x, M, w1, b1, w2, b2, eps, out_f32, out_hi, out_lo, hi_fp16, f32_row_out);  \
     break;
   switch (D / 128) {
     IEF_LN(1) IEF_LN(2) IEF_LN(3) IEF_LN(4) IEF_LN(5) IEF_LN(6) IEF_LN(7) IEF_LN(8)
@@ -361,6 +375,17 @@ int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long ro
   IEF_CHECK(D % 8 == 0, "gather_rows: D=%d must be a multiple of 8", D);
   if (n_rows == 0) return IEFVAD_OK;
   gather_rows_kernel<<<grid_for(n_rows * 32, num_sms), kThreads, 0, stream>>>(ctx, x, rowmap, row_base, n_rows, D, ctx_c, x_c);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int inverse_rowmap(const int* rowmap, long long row_base, long long n_rows, long long M, int* inv, int num_sms,
+                   cudaStream_t stream) {
+  if (M == 0) return IEFVAD_OK;
+  IEF_CUDA(cudaMemsetAsync(inv, 0xFF, size_t(M) * sizeof(int), stream));        // -1 = row does not survive
+  if (n_rows == 0) return IEFVAD_OK;
+  inverse_rowmap_kernel<<<grid_for(n_rows, num_sms), kThreads, 0, stream>>>(rowmap, row_base, n_rows, inv);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

@@ -18,7 +18,12 @@ int ingest_ragged(const void* packed, int dtype, const long long* chunk_start, l
 // out = LN(x; w1, b1) or LN(LN(x; w1, b1); w2, b2) when w2 != null.  x [M, D] fp32.
 int layernorm(const float* x, long long M, int D, const float* w1, const float* b1, const float* w2, const float* b2,
               float eps, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms, cudaStream_t stream,
-              int hi_fp16 = 0 /* out_hi receives fp16 instead of bf16 (no lo) */);
+              int hi_fp16 = 0 /* out_hi receives fp16 instead of bf16 (no lo) */,
+              const int* f32_row_out = nullptr /* [M]: row of out_f32 that receives source row r, < 0 = none */);
+
+// inv[rowmap[j] - row_base] = j for j < n_rows, every other entry of inv[0, M) = -1
+int inverse_rowmap(const int* rowmap, long long row_base, long long n_rows, long long M, int* inv, int num_sms,
+                   cudaStream_t stream);
 
 // model/imf_vad.py:130-144.  n elements; fused / fused_hi / fused_lo optional.
 int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long n, float factor,

@@ -287,6 +287,13 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
         Mo += vr->len_host[b];
       }
     }
+    // valid-rows mode with >= 2 layers: the producers of the last layer's out-projection inputs write compact rows
+    // themselves (LayerNorm of layer L-2: fp32 residual; last attention core: context) - no gather pass
+    const bool direct_compact = vr && L >= 2;
+    if (direct_compact) {
+      IEF_TRY(inv_map.reserve(size_t(M) * sizeof(int)));
+      IEF_TRY(inverse_rowmap(vr->rowmap + out0, vr->row_base + row0, Mo, M, inv_map.as<int>(), num_sms, stream));
+    }
     for (int m = 0; m < 2; ++m) {
       const bool ragged = vr && vr->chunk_start && vr->chunk_valid;
       const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + (ragged ? 0 : size_t(row0) * D * in_esize);
@@ -329,6 +336,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           at.q = qb.as<bf16>(); at.k = kb.as<bf16>(); at.vt = vtb.as<bf16>(); at.out = h_hi.as<bf16>(); at.ldo = D;
           at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
           at.fp16 = a16; at.out_fp16 = a16;
+          if (direct_compact && last) at.row_out = inv_map.as<int>();
           IEF_PROF(KC_ATTN_TC, 4.0 * M * T * D, attn_tc(at, stream));
           // after the last attention core only the valid rows go on: gather (context, residual) into compact matrices
           const bool compact = vr && last;
@@ -336,7 +344,9 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           const bf16* ctx = h_hi.as<bf16>();
           const float* resid = x32.as<float>();
           float* yout = y32.as<float>();
-          if (compact) {
+          if (compact && direct_compact) {
+            resid = x32.as<float>(); yout = y32.as<float>();       // both already compact
+          } else if (compact) {
             IEF_PROF(KC_GATHER, double(Mo) * D * 12, gather_rows(h_hi.as<bf16>(), x32.as<float>(), vr->rowmap + out0,
                      vr->row_base + row0, Mo, D, h_lo.as<bf16>(), y32.as<float>(), num_sms, stream));
             ctx = h_lo.as<bf16>(); resid = y32.as<float>(); yout = x32.as<float>();
@@ -353,7 +363,8 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
             const bool need_lo = last ? (!h16 && (plan & PLAN_SPLIT_HEADS) != 0) : sp;
             IEF_PROF(KC_LAYERNORM, double(Mc) * D * 8, layernorm(yout, Mc, D, ln_w[m][i], ln_b[m][i], last ? whiten_w[m] : nullptr,
                               last ? whiten_b[m] : nullptr, 1e-5f, last ? nullptr : x32.as<float>(), a_hi.as<bf16>(),
-                              need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream, ((a16 && !last) || (h16 && last)) ? 1 : 0));
+                              need_lo ? a_lo.as<bf16>() : nullptr, num_sms, stream, ((a16 && !last) || (h16 && last)) ? 1 : 0,
+                              (direct_compact && i == L - 2) ? inv_map.as<int>() : nullptr));
           }
         }
       }
@@ -429,7 +440,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
 
 void Model::destroy() {
   DevBuf* all[] = {&params_f32, &params_hi, &params_lo, &params_h16, &x32, &y32, &a_hi, &a_lo, &h_hi, &h_lo,
-                   &qb, &kb, &vtb, &qkv32, &attn32, &h32};
+                   &qb, &kb, &vtb, &qkv32, &attn32, &h32, &inv_map};
   for (DevBuf* b : all) b->release();
 }
 

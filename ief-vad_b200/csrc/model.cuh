@@ -88,7 +88,7 @@ struct Model {
   DevBuf params_f32, params_hi, params_lo, params_h16;
 
   // workspace (one slab)
-  DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32;
+  DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32, inv_map;
   long long ws_rows = 0;
   int ws_T = 0;
 
