@@ -213,6 +213,14 @@ fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, co
       u.x = *reinterpret_cast<const uint32_t*>(&h01);
       u.y = *reinterpret_cast<const uint32_t*>(&h23);
       *reinterpret_cast<uint2*>(fused_hi + i * 4) = u;
+      if (fused_lo) {                           // fp16 remainder: hi + lo carries the residual stream (~22 bits)
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(f[0] - f01.x, f[1] - f01.y), l23 = __floats2half2_rn(f[2] - f23.x, f[3] - f23.y);
+        uint2 ul;
+        ul.x = *reinterpret_cast<const uint32_t*>(&l01);
+        ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(fused_lo + i * 4) = ul;
+      }
     } else if (fused_hi) {
       bf16 h[4], l[4];
 #pragma unroll

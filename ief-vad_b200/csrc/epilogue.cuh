@@ -15,6 +15,10 @@ struct EpiParams {
   // out = (resid ? resid[row, col] : 0) + alpha * act(acc + bias)
   const float* resid = nullptr;  // fp32 [M, ld_resid] or null
   int ld_resid = 0;
+  // tcgen05 path only: the residual as fp16 [M, ld_resid] (exact for fp16 inputs), optionally plus an fp16 remainder
+  // (resid = hi + lo, ~22 mantissa bits); replaces `resid`
+  const void* resid_h16 = nullptr;
+  const void* resid_l16 = nullptr;
   float alpha = 1.f;
   // row-major outputs (any subset)
   float* out_f32 = nullptr;      // columns [0, split_col)

@@ -60,6 +60,8 @@ struct TcEpi {
   int stages = 4;
   uint32_t idesc = 0;      // tcgen05 instruction descriptor (operand format bf16 / fp16, tile shape)
   int hi_fp16 = 0;         // the 16-bit output is fp16 instead of bf16
+  uint32_t rslot = kF32Box; // bytes per residual ring slot
+  int resid_lo = 0;        // R16 instances: the fp16 residual has a remainder part (second box of the ring slot)
   // EPI_QKV
   bf16* q = nullptr;
   bf16* k = nullptr;
@@ -71,7 +73,8 @@ struct TcEpi {
 
 struct TcMaps {
   CUtensorMap a0, a1, b0, b1;   // operands (hi / lo)
-  CUtensorMap r;                // fp32 residual [M, N]
+  CUtensorMap r;                // fp32 residual [M, N] (R16 instances: its fp16 form, r2 = fp16 remainder)
+  CUtensorMap r2;
   CUtensorMap o0, o1;           // fp32 outputs (columns below / from split_col)
   CUtensorMap h, l;             // bf16 hi / lo outputs; in EPI_QKV: q / k as 4-D {d, t, head, batch}
 };
@@ -99,7 +102,8 @@ __device__ __forceinline__ uint32_t sw64(int row, int g) { return uint32_t(row) 
 // (mainloop ~80 % of the tensor rate, and every epilogue byte staged through smem slows it further).  Only the
 // leader CTA issues MMAs; its commits multicast to the mbarriers of both CTAs; both producers signal the leader's
 // `full` barrier; both epilogues arrive on the leader's `tempty`.
-template <int BN, int MODE, int ACT, int CG>
+// R16: the residual arrives as fp16 (+ optional fp16 remainder) boxes instead of fp32 ones.
+template <int BN, int MODE, int ACT, int CG, int R16>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nsplit, const TcEpi ep) {
   using Cfg = TcCfg<BN, CG>;
@@ -221,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     const int par = (warp - 2) >> 2;      // the two warps of a quarter split the column chunks: c = par, par + 2, ...
     uint8_t* wb = epi_base + size_t(warp - 2) * ep.warp_bytes;
     uint8_t* Rb = wb;                                                      // [nr] fp32 residual (/ in-place output) boxes
-    uint8_t* Ob = Rb + size_t(ep.nr) * kF32Box;                            // [2] fp32 output boxes (no residual ring)
+    uint8_t* Ob = Rb + size_t(ep.nr) * ep.rslot;                            // [2] fp32 output boxes (no residual ring)
     uint8_t* Hb = Ob + ((ep.has_f32 && !ep.inplace) ? 2 * kF32Box : 0);    // [2] bf16 hi (or q / k) boxes
     uint8_t* Lb = Hb + (ep.has_hi ? 2 * kBfBox : 0);                       // [2] bf16 lo boxes
     uint64_t* rfull = rfull_all + (warp - 2) * kMaxResidSlots;
@@ -239,8 +243,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       if (pf_tile >= num_tiles) return;
       const int m_blk = (pf_tile / num_n) * CG + int(rank), n_blk = pf_tile % num_n;
       const int slot = int(pf_n % uint32_t(ep.nr));
-      mbar_arrive_expect_tx(&rfull[slot], kF32Box);
-      tma_load_2d(&tm.r, &rfull[slot], Rb + size_t(slot) * kF32Box, n_blk * BN + pf_c * CW, m_blk * BM + quarter * 32);
+      if (R16) {
+        mbar_arrive_expect_tx(&rfull[slot], ep.resid_lo ? 2 * kBfBox : kBfBox);
+        tma_load_2d(&tm.r, &rfull[slot], Rb + size_t(slot) * ep.rslot, n_blk * BN + pf_c * CW, m_blk * BM + quarter * 32);
+        if (ep.resid_lo)
+          tma_load_2d(&tm.r2, &rfull[slot], Rb + size_t(slot) * ep.rslot + kBfBox, n_blk * BN + pf_c * CW,
+                      m_blk * BM + quarter * 32);
+      } else {
+        mbar_arrive_expect_tx(&rfull[slot], kF32Box);
+        tma_load_2d(&tm.r, &rfull[slot], Rb + size_t(slot) * ep.rslot, n_blk * BN + pf_c * CW, m_blk * BM + quarter * 32);
+      }
       ++pf_n;
       pf_c += 2;
       while (pf_tile < num_tiles && pf_c >= chunks_of(pf_tile)) { pf_c = par; pf_tile += tile_step; }
@@ -248,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
     while (pf_tile < num_tiles && pf_c >= chunks_of(pf_tile)) pf_tile += tile_step;   // tiles too narrow for this parity
     if (ep.has_resid && lane == 0) {
       tma_prefetch_desc(&tm.r);
+      if (R16 && ep.resid_lo) tma_prefetch_desc(&tm.r2);
       for (int i = 0; i < ep.nr; ++i) prefetch_resid();
     }
     uint32_t n_cons = 0;       // residual chunks consumed
@@ -345,14 +358,39 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       if (ep.has_resid) {
         const int slot = int(n_cons % uint32_t(ep.nr));
         mbar_wait(&rfull[slot], (n_cons / uint32_t(ep.nr)) & 1);
-        uint8_t* rb = Rb + size_t(slot) * kF32Box;
+        uint8_t* rb = Rb + size_t(slot) * ep.rslot;
+        if (R16) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128(lane, g));
-          v[g * 4 + 0] = fmaf(ep.alpha, v[g * 4 + 0], r4.x);
-          v[g * 4 + 1] = fmaf(ep.alpha, v[g * 4 + 1], r4.y);
-          v[g * 4 + 2] = fmaf(ep.alpha, v[g * 4 + 2], r4.z);
-          v[g * 4 + 3] = fmaf(ep.alpha, v[g * 4 + 3], r4.w);
+          for (int g = 0; g < 4; ++g) {
+            const uint4 h4 = *reinterpret_cast<const uint4*>(rb + sw64(lane, g));
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+            float r[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
+              r[2 * q] = f.x; r[2 * q + 1] = f.y;
+            }
+            if (ep.resid_lo) {
+              const uint4 l4 = *reinterpret_cast<const uint4*>(rb + kBfBox + sw64(lane, g));
+              const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&lw[q]));
+                r[2 * q] += f.x; r[2 * q + 1] += f.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] = fmaf(ep.alpha, v[g * 8 + j], r[j]);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128(lane, g));
+            v[g * 4 + 0] = fmaf(ep.alpha, v[g * 4 + 0], r4.x);
+            v[g * 4 + 1] = fmaf(ep.alpha, v[g * 4 + 1], r4.y);
+            v[g * 4 + 2] = fmaf(ep.alpha, v[g * 4 + 2], r4.z);
+            v[g * 4 + 3] = fmaf(ep.alpha, v[g * 4 + 3], r4.w);
+          }
         }
         ++n_cons;
         if (ep.inplace) {
@@ -384,7 +422,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
             if (ep.hi_fp16) {
               const __half2 h2 = __floats2half2_rn(a, b);
               hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[q] = 0u;
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);     // fp16 remainder: hi + lo ~ 22 mantissa bits
+              lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
             } else {
               const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
               hi[q] = pack_bf16x2(ah, bh);
@@ -454,11 +494,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
   }
 }
 
-template <int BN, int MODE, int ACT, int CG>
+template <int BN, int MODE, int ACT, int CG, int R16 = 0>
 int launch_inst(const TcMaps& tm, const GemmTcArgs& g, const TcEpi& e, int grid, size_t smem_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, ACT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IEF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, ACT, CG, R16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   int(kSmemLimit)));
     attr_set = true;
   }
@@ -475,7 +515,7 @@ int launch_inst(const TcMaps& tm, const GemmTcArgs& g, const TcEpi& e, int grid,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IEF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, ACT, CG>, tm, g.M, g.N, g.K, g.nsplit, e));
+  IEF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, ACT, CG, R16>, tm, g.M, g.N, g.K, g.nsplit, e));
   count_launches(1);
   return IEFVAD_OK;
 }
@@ -488,18 +528,22 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   e.idesc = g.fp16 ? make_idesc_f16(BM * CG, BN) : make_idesc_bf16(BM * CG, BN);
   e.hi_fp16 = ep.hi_fp16;
   IEF_CHECK(!g.fp16 || g.nsplit == 1, "gemm_tc: fp16 operands are single-pass (nsplit == 1)");
-  IEF_CHECK(!ep.hi_fp16 || ep.out_lo == nullptr, "gemm_tc: an fp16 output has no lo part");
+  const bool r16 = ep.resid_h16 != nullptr;
+  IEF_CHECK(!r16 || (ep.resid == nullptr && ep.mode == EPI_ROWMAJOR && ep.act == ACT_NONE),
+            "gemm_tc: the fp16 residual replaces the fp32 one (row-major epilogue, no activation)");
+  IEF_CHECK(r16 || ep.resid_l16 == nullptr, "gemm_tc: resid_l16 without resid_h16");
   TcMaps tm;
   memset(&tm, 0, sizeof(tm));
   if (ep.mode == EPI_ROWMAJOR) {
-    e.has_resid = ep.resid != nullptr;
+    e.has_resid = ep.resid != nullptr || r16;
+    e.resid_lo = ep.resid_l16 != nullptr;
     e.has_f32 = ep.out_f32 != nullptr;
     e.has_hi = ep.out_hi != nullptr;
     e.has_lo = ep.out_hi != nullptr && ep.out_lo != nullptr;
     IEF_CHECK(ep.split_col % CW == 0 || ep.split_col >= g.N, "gemm_tc: split_col must be a multiple of %d", CW);
     IEF_CHECK(!e.has_f32 || (ep.ld_f32 % 4 == 0), "gemm_tc: ld_f32 must be a multiple of 4");
     IEF_CHECK(!e.has_hi || (ep.ld_bf % 8 == 0), "gemm_tc: ld_bf must be a multiple of 8");
-    IEF_CHECK(!e.has_resid || (ep.ld_resid % 4 == 0), "gemm_tc: ld_resid must be a multiple of 4");
+    IEF_CHECK(!e.has_resid || (ep.ld_resid % (r16 ? 8 : 4) == 0), "gemm_tc: ld_resid must be a multiple of 4 (fp16: 8)");
   } else if (ep.mode == EPI_QKV) {
     IEF_CHECK(ep.q && ep.k && ep.vt, "gemm_tc: QKV epilogue needs q, k and vt");
     IEF_CHECK(ep.D % CW == 0 && ep.dh % CW == 0 && g.N == 3 * ep.D && ep.T > 0,
@@ -511,9 +555,10 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   }
   // per-warp epilogue smem: a residual ring whose slots double as the fp32 output boxes (in place), else two fp32
   // output boxes; bf16 boxes always ping-pong
-  e.inplace = (e.has_resid && e.has_f32) ? 1 : 0;
-  e.nr = e.has_resid ? (e.has_lo ? 2 : 3) : 0;      // the widest epilogue (fp32 + hi + lo) trades ring depth for a stage
-  e.warp_bytes = e.nr * kF32Box + ((e.has_f32 && !e.inplace) ? 2 * kF32Box : 0) + (e.has_hi ? 2 * kBfBox : 0) +
+  e.inplace = (e.has_resid && e.has_f32 && !r16) ? 1 : 0;
+  e.nr = e.has_resid ? ((e.has_lo || r16) ? 2 : 3) : 0;   // the widest epilogues trade ring depth for an operand stage
+  e.rslot = r16 ? (e.resid_lo ? 2 * kBfBox : kBfBox) : kF32Box;
+  e.warp_bytes = e.nr * e.rslot + ((e.has_f32 && !e.inplace) ? 2 * kF32Box : 0) + (e.has_hi ? 2 * kBfBox : 0) +
                  (e.has_lo ? 2 * kBfBox : 0);
   const uint32_t fixed = 1024 + kEpiWarps * e.warp_bytes + kBarBytes;
   int stages = int((kSmemLimit - fixed) / Cfg::kStageBytes);
@@ -532,7 +577,11 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
     tm.a1 = tm.a0;
     tm.b1 = tm.b0;
   }
-  if (e.has_resid)
+  if (r16) {
+    IEF_TRY(make_tmap_2d(&tm.r, ep.resid_h16, g.N, g.M, uint64_t(ep.ld_resid) * 2, CW, 32, TM_BF16, TM_SWIZZLE_64B));
+    if (e.resid_lo)
+      IEF_TRY(make_tmap_2d(&tm.r2, ep.resid_l16, g.N, g.M, uint64_t(ep.ld_resid) * 2, CW, 32, TM_BF16, TM_SWIZZLE_64B));
+  } else if (e.has_resid)
     IEF_TRY(make_tmap_2d(&tm.r, ep.resid, g.N, g.M, uint64_t(ep.ld_resid) * 4, CW, 32, TM_F32, TM_SWIZZLE_128B));
   if (e.has_f32) {
     const uint64_t w0 = ep.split_col < g.N ? ep.split_col : g.N;
@@ -564,6 +613,7 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
     IEF_CHECK(ep.act == ACT_NONE, "gemm_tc: the QKV epilogue has no activation");
     return launch_inst<BN, EPI_QKV, ACT_NONE, CG>(tm, g, e, grid, smem_bytes, stream);
   }
+  if (r16) return launch_inst<BN, EPI_ROWMAJOR, ACT_NONE, CG, 1>(tm, g, e, grid, smem_bytes, stream);
   switch (ep.act) {       // EPI_DISCARD runs the row-major instance and drops the accumulator
     case ACT_NONE: return launch_inst<BN, EPI_ROWMAJOR, ACT_NONE, CG>(tm, g, e, grid, smem_bytes, stream);
     case ACT_RELU: return launch_inst<BN, EPI_ROWMAJOR, ACT_RELU, CG>(tm, g, e, grid, smem_bytes, stream);
