@@ -12,5 +12,5 @@ echo "launch list: $(wc -l < gpurun_out/launches.csv) lines"
 # refinement GEMMs of the 4th forward: per forward 10 encoder/head GEMMs precede the 20 refinement GEMMs
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 100 -c 4 -f -o gpurun_out/bench_gemm_refine $CMD > gpurun_out/prof_ncu_full.log 2>&1
 tail -1 gpurun_out/prof_ncu_full.log
-ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 12 -c 1 -f -o gpurun_out/bench_attn $CMD > gpurun_out/prof_ncu_attn.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attn_short -s 12 -c 1 -f -o gpurun_out/bench_attn $CMD > gpurun_out/prof_ncu_attn.log 2>&1
 tail -1 gpurun_out/prof_ncu_attn.log
