@@ -15,6 +15,10 @@ struct AttnTcArgs {
   int fp16 = 0;                        // q / k / vt hold fp16 and P is rounded to fp16 (11-bit mantissa), else bf16
   int out_fp16 = 0;                    // `out` receives fp16 instead of bf16
   const int* row_out = nullptr;        // optional [B*T]: output row of query row b*T+t (compact layouts), < 0 = drop
+  // ragged items (short kernel only): q / k are [H, T, dhp], vt [H, dh, Tpad] over ALL packed rows and items[c] =
+  // {first row, rows (<= 256), valid rows, multiplicity of the last row as a key (0 = none)} for n_chunks row ranges
+  const int* items = nullptr;          // device, int4 per chunk
+  int n_chunks = 0;
   int key_block = 0;                   // 0 = heuristic (64 keys per block up to T = 2048, else 128), or 64 / 128
 };
 

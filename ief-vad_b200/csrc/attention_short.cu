@@ -91,7 +91,8 @@ template <int DH, int DHP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H, int n_items,
-                  int fp16, int out_fp16, const int* __restrict__ row_out, long long* __restrict__ trace) {
+                  int fp16, int out_fp16, const int* __restrict__ row_out, const int4* __restrict__ items,
+                  long long* __restrict__ trace) {
   using Cfg = ShortCfg<DH, DHP>;
   // debug timeline (IEFVAD_ATTN_TRACE): CTA 0 records clock64() of pipeline events, 16 slots per item
   auto mark = [&](int it, int ev) { if (trace && blockIdx.x == 0 && it < 64) trace[it * 16 + ev] = clock64(); };
@@ -110,6 +111,27 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   float* xch = reinterpret_cast<float*>(smem + Cfg::kOffX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Work item -> (first row, rows, valid rows, multiplicity of the last row as a key, tensor-map z coordinate).
+  // Dense batches: item = b * H + h over [B*H, T, dhp]; ragged ("items"): item = chunk * H + h over [H, Mtot, dhp],
+  // chunk c owning rows [start, start + rows) of which the last one, when mult > 0, stands for `mult` identical
+  // zero-pad rows (it enters the softmax with log(mult) added to its score).
+  struct Item { int row0, rows, valid, mult, z, orow0; };
+  auto get_item = [&](int item) {
+    Item d;
+    if (items) {
+      const int c = item / H;
+      const int4 v = __ldg(items + c);
+      d.row0 = v.x; d.rows = v.y; d.valid = v.z; d.mult = v.w; d.z = item - c * H; d.orow0 = v.x;
+    } else {
+      const int b = item / H;
+      d.row0 = 0; d.rows = T; d.valid = T; d.mult = 0; d.z = item; d.orow0 = b * T;
+    }
+    return d;
+  };
+  // stale K / V rows of earlier items stay in shared memory when a short item loads fewer boxes: they only ever meet
+  // P == 0, but must be finite - so the operand buffers start out as zeros
+  for (uint32_t i = threadIdx.x * 16u; i < Cfg::kOffX; i += kThreads * 16u) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
 
   if (warp == kSoftmaxWarps && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -139,39 +161,50 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == kSoftmaxWarps) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      auto nq = [](const Item& d) { return d.rows > 128 ? 2 : 1; };                    // 128-row Q / K boxes
+      auto nv = [](const Item& d) { return (d.rows + 63) >> 6; };                      // 64-key V^T boxes
+      auto load_qk = [&](const Item& d) {
+        mbar_arrive_expect_tx(qk_full, uint32_t(nq(d)) * (Cfg::kQTile + Cfg::kKBytes / 2));
+        for (int t = 0; t < nq(d); ++t)
+#pragma unroll
+          for (int c = 0; c < DHP / 64; ++c) {
+            tma_load_3d(&tmQ, qk_full, smem + t * Cfg::kQTile + c * Cfg::kQChunk, c * 64, d.row0 + t * 128, d.z);
+            tma_load_3d(&tmK, qk_full, smem + Cfg::kOffK + c * Cfg::kKChunk + t * Cfg::kQChunk, c * 64, d.row0 + t * 128, d.z);
+          }
+      };
+      auto prefetch = [&](const Item& nx) {
+        for (int t = 0; t < nq(nx); ++t)
+#pragma unroll
+          for (int c = 0; c < DHP / 64; ++c) {
+            tma_prefetch_3d(&tmQ, c * 64, nx.row0 + t * 128, nx.z);
+            tma_prefetch_3d(&tmK, c * 64, nx.row0 + t * 128, nx.z);
+          }
+        for (int c = 0; c < nv(nx); ++c) tma_prefetch_3d(&tmVt, nx.row0 + c * 64, 0, nx.z);
+      };
+      // The S MMAs read Q and K from shared memory at three quarters of its bandwidth: a TMA load landing at the same
+      // time slows them down (measured: S issue -> S visible 1.1 k cycles alone, 2.6 k beside the V load).  So V(i)
+      // starts when S_a(i) has retired (it is needed after the softmax), Q / K (i+1) when all S MMAs of item i have.
+      const int step = int(gridDim.x);
+      if (int(blockIdx.x) < n_items) {
+        load_qk(get_item(blockIdx.x));
+        if (int(blockIdx.x) + step < n_items) prefetch(get_item(blockIdx.x + step));
+      }
       int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < n_items; item += step, ++it) {
         const uint32_t ph = it & 1;
-        mbar_wait(qk_empty, ph ^ 1);
-        mark(it, 0);
-        mbar_arrive_expect_tx(qk_full, 2 * Cfg::kQTile + Cfg::kKBytes);
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-          for (int c = 0; c < DHP / 64; ++c)
-            tma_load_3d(&tmQ, qk_full, smem + t * Cfg::kQTile + c * Cfg::kQChunk, c * 64, t * 128, item);
-#pragma unroll
-        for (int c = 0; c < DHP / 64; ++c)
-          tma_load_3d(&tmK, qk_full, smem + Cfg::kOffK + c * Cfg::kKChunk, c * 64, 0, item);
-        // the next item starts streaming from HBM into L2 now: its shared-memory loads (issued when the S / P.V
-        // MMAs of this item have retired) then only pay the L2 latency
-        if (item + int(gridDim.x) < n_items) {
-          const int nx = item + int(gridDim.x);
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int c = 0; c < DHP / 64; ++c) tma_prefetch_3d(&tmQ, c * 64, t * 128, nx);
-#pragma unroll
-          for (int c = 0; c < DHP / 64; ++c) tma_prefetch_3d(&tmK, c * 64, 0, nx);
-#pragma unroll
-          for (int c = 0; c < Cfg::TK / 64; ++c) tma_prefetch_3d(&tmVt, c * 64, 0, nx);
-        }
-        mbar_wait(v_empty, ph ^ 1);
+        const Item d = get_item(item);
+        mbar_wait(&s_full[0], ph);                // S_a(i) retired
+        mbar_wait(v_empty, ph ^ 1);               // P.V of item i-1 retired
         mark(it, 1);
-        mbar_arrive_expect_tx(v_full, Cfg::kVBytes);
-#pragma unroll
-        for (int c = 0; c < Cfg::TK / 64; ++c)
-          tma_load_3d(&tmVt, v_full, smem + Cfg::kOffV + c * Cfg::kVSub, c * 64, 0, item);
+        mbar_arrive_expect_tx(v_full, uint32_t(nv(d)) * Cfg::kVSub);
+        for (int c = 0; c < nv(d); ++c)
+          tma_load_3d(&tmVt, v_full, smem + Cfg::kOffV + c * Cfg::kVSub, d.row0 + c * 64, 0, d.z);
+        if (item + step < n_items) {
+          mbar_wait(qk_empty, ph);                // every S MMA of item i retired: Q / K buffers are free
+          mark(it + 1, 0);
+          load_qk(get_item(item + step));
+          if (item + 2 * step < n_items) prefetch(get_item(item + 2 * step));
+        }
       }
     }
   } else if (warp == kSoftmaxWarps + 1) {
@@ -203,36 +236,46 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       };
       // The two query tiles run half an item apart: S_a(i), P.V_b(i-1), S_b(i), P.V_a(i).  While tile a's softmax
       // owns the SFU, the tensor pipe serves tile b, and vice versa (in lock-step both would wait at the same time).
+      // Items of <= 128 rows have no tile b; tile b's barriers count only the items that use it.
       int it = 0;
+      uint32_t nb_s = 0, nb_pv = 0;           // S_b / P.V_b issued so far
+      bool pend_b = false;                    // the previous item still owes its P.V_b
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
+        const bool act_b = get_item(item).rows > 128;
         mbar_wait(qk_full, ph);
         mark(it, 2);
         mbar_wait(&s_empty[0], ph ^ 1);         // tile 0's columns (P and O of the previous item) have been read out
         mark(it, 3);
         tc_fence_after();
         issue_s(0);
-        if (it > 0) {
-          mbar_wait(&p_full[1], ph ^ 1);
+        if (pend_b) {
+          mbar_wait(&p_full[1], nb_pv & 1);
           mark(it - 1, 7);
           tc_fence_after();
           issue_pv(1);                          // previous item, still on the previous V
           tc_commit(v_empty);
+          ++nb_pv;
         }
-        mbar_wait(&s_empty[1], ph ^ 1);
-        mark(it, 4);
-        tc_fence_after();
-        issue_s(1);
-        tc_commit(qk_empty);                    // Q and K may be overwritten once both S MMAs have retired
+        if (act_b) {
+          mbar_wait(&s_empty[1], (nb_s & 1) ^ 1);
+          mark(it, 4);
+          tc_fence_after();
+          issue_s(1);
+          ++nb_s;
+        }
+        tc_commit(qk_empty);                    // Q and K may be overwritten once the S MMAs have retired
         mbar_wait(v_full, ph);
         mark(it, 5);
         mbar_wait(&p_full[0], ph);
         mark(it, 6);
         tc_fence_after();
         issue_pv(0);
+        if (!act_b) tc_commit(v_empty);
+        pend_b = act_b;
       }
-      if (it > 0) {
-        mbar_wait(&p_full[1], (it - 1) & 1);
+      if (pend_b) {
+        mbar_wait(&p_full[1], nb_pv & 1);
         tc_fence_after();
         issue_pv(1);
       }
@@ -248,35 +291,47 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t ts = tbase + uint32_t(hf * 128);
     const uint32_t tp = tbase + (hf ? Cfg::kColP1 : Cfg::kColP0);
     const int key0 = hf * 128;
-    const bool tail = T < Cfg::TK;
     // exchange slots: xch[((kind * 2 + parity) * 2 + tile) * 2 + half][row]
     auto slot = [&](int kind, uint32_t ph, int half) { return xch + ((((kind * 2 + int(ph)) * 2 + t) * 2 + half) << 7) + r; };
 
     int it = 0;
+    uint32_t n_mine = 0;                            // items this tile has processed (tile 1 skips the short ones)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint32_t ph = it & 1;
-      const int b = item / H, h = item - b * H;
+      const Item d = get_item(item);
+      if (t == 1 && d.rows <= 128) continue;
+      const uint32_t ph = n_mine & 1;
+      ++n_mine;
+      const int h = items ? d.z : item % H;
+      const int Tk = d.rows;                        // keys of this item
+      const int padkey = d.mult > 0 ? d.valid : -1; // the key that stands for `mult` identical zero-pad rows
+      const float lnm = d.mult > 0 ? __logf(float(d.mult)) : 0.f;
+      const int plain_end = padkey >= 0 ? padkey : Tk;   // 32-key chunks that end at or before this key need no masking
       mbar_wait(&s_full[t], ph);
       if (threadIdx.x == 0 || threadIdx.x == 256) mark(it, 8 + t);
       tc_fence_after();
-      // ---- pass 1: row max over this thread's 128 keys
+      // ---- pass 1: row max over this thread's 128 keys.  Only the 32-key chunk that holds the last key needs per-key
+      // masking (keys >= Tk are not there; the last key may carry a multiplicity); chunks before it are plain, chunks
+      // after it are skipped.  All of this is warp-uniform.
       float mx = -INFINITY;
+      auto chunk_max = [&](const float (&v)[32], int k_lo) {
+        if (k_lo + 32 <= plain_end) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+        } else if (k_lo < Tk) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (k_lo + i < Tk) mx = fmaxf(mx, k_lo + i == padkey ? v[i] + lnm : v[i]);
+        }
+      };
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
+        if (key0 + c2 * 64 >= Tk) break;
         float v0[32], v1[32];
         tmem_ld32(ts + uint32_t(c2 * 64), v0);
         tmem_ld32(ts + uint32_t(c2 * 64 + 32), v1);
         tmem_ld_wait();
-        if (tail) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (key0 + c2 * 64 + i < T) mx = fmaxf(mx, v0[i]);
-            if (key0 + c2 * 64 + 32 + i < T) mx = fmaxf(mx, v1[i]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(v0[i], v1[i]));
-        }
+        chunk_max(v0, key0 + c2 * 64);
+        chunk_max(v1, key0 + c2 * 64 + 32);
       }
       *slot(0, ph, hf) = mx;
       named_bar_sync(1 + t, 256);
@@ -289,20 +344,36 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c = hf ? 3 - ci : ci;
-        float v[32];
-        tmem_ld32(ts + uint32_t(c * 32), v);
-        tmem_ld_wait();
+        const int k_lo = key0 + c * 32;
         uint32_t pk[16];
+        if (k_lo >= Tk) {                            // no key here: P = 0 (the MMA still reads these columns)
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(v[i], kLog2e, -mscaled));
-          float p1 = fast_exp2(fmaf(v[i + 1], kLog2e, -mscaled));
-          if (tail) {
-            if (key0 + c * 32 + i >= T) p0 = 0.f;
-            if (key0 + c * 32 + i + 1 >= T) p1 = 0.f;
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        } else {
+          float v[32];
+          tmem_ld32(ts + uint32_t(c * 32), v);
+          tmem_ld_wait();
+          if (k_lo + 32 <= plain_end) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = fast_exp2(fmaf(v[i], kLog2e, -mscaled));
+              const float p1 = fast_exp2(fmaf(v[i + 1], kLog2e, -mscaled));
+              lsum += p0 + p1;
+              pk[i >> 1] = pack_16x2(p0, p1, fp16);
+            }
+          } else {                                   // the chunk with the last key
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float x0 = (k_lo + i == padkey) ? v[i] + lnm : v[i];
+              const float x1 = (k_lo + i + 1 == padkey) ? v[i + 1] + lnm : v[i + 1];
+              float p0 = fast_exp2(fmaf(x0, kLog2e, -mscaled));
+              float p1 = fast_exp2(fmaf(x1, kLog2e, -mscaled));
+              if (k_lo + i >= Tk) p0 = 0.f;
+              if (k_lo + i + 1 >= Tk) p1 = 0.f;
+              lsum += p0 + p1;
+              pk[i >> 1] = pack_16x2(p0, p1, fp16);
+            }
           }
-          lsum += p0 + p1;
-          pk[i >> 1] = pack_16x2(p0, p1, fp16);
         }
         tmem_st16(tp + uint32_t(c * 16), pk);
       }
@@ -324,9 +395,9 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       mbar_arrive(&s_empty[t]);
       if (threadIdx.x == 0) mark(it, 14);
-      long long ro = (long long)b * T + tq;
-      if (tq < T && row_out) ro = __ldg(row_out + ro);
-      if (tq < T && ro >= 0) {
+      long long ro = (long long)d.orow0 + tq;
+      if (tq < Tk && row_out) ro = __ldg(row_out + ro);
+      if (tq < Tk && ro >= 0) {
         bf16* dst = out + ro * ldo + h * DH + hf * (DH / 2);
 #pragma unroll
         for (int d = 0; d < DH / 2; d += 8) {
@@ -358,12 +429,13 @@ int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
                                   static_cast<int>(Cfg::kSmemBytes)));
     attr_set = true;
   }
-  const uint64_t BH = uint64_t(a.B) * a.H;
+  // dense: [B*H, T, dhp]; ragged items: [H, T = all packed rows, dhp] with `n_chunks` row ranges (AttnTcArgs.items)
+  const uint64_t BH = a.items ? uint64_t(a.H) : uint64_t(a.B) * a.H;
   CUtensorMap tq, tk, tv;
   IEF_TRY(make_tmap_3d(&tq, a.q, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, 128, 1));
-  IEF_TRY(make_tmap_3d(&tk, a.k, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, Cfg::TK, 1));
+  IEF_TRY(make_tmap_3d(&tk, a.k, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, 128, 1));
   IEF_TRY(make_tmap_3d(&tv, a.vt, a.T, DH, BH, uint64_t(a.Tpad) * 2, uint64_t(DH) * a.Tpad * 2, 64, DH, 1));
-  const int n_items = int(BH);
+  const int n_items = a.items ? a.n_chunks * a.H : int(BH);
   const int grid = n_items < num_sms ? n_items : num_sms;
   static const bool want_trace = getenv("IEFVAD_ATTN_TRACE") != nullptr;
   static long long* trace = nullptr;
@@ -373,7 +445,8 @@ int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
     for (int i = 0; i < 64 * 16; ++i) trace[i] = 0;
   }
   attn_short_kernel<DH, DHP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, n_items,
-                                                                         a.fp16, a.out_fp16, a.row_out, (want_trace && traced < 3) ? trace : nullptr);
+                                                                         a.fp16, a.out_fp16, a.row_out, reinterpret_cast<const int4*>(a.items),
+                                                                         (want_trace && traced < 3) ? trace : nullptr);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   if (want_trace && traced < 3 && n_items >= 8 * grid) {
@@ -394,6 +467,7 @@ int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
 
 bool attn_short_supported(const AttnTcArgs& a) {
   static const int env_off = [] { const char* e = getenv("IEFVAD_ATTN_SHORT"); return (e && atoi(e) == 0) ? 1 : 0; }();
+  if (a.items) return !a.attn_mask && !a.key_pad;      // ragged items exist only here (every item <= 256 rows)
   return !env_off && a.T <= 256 && !a.attn_mask && !a.key_pad && uint64_t(a.B) * a.H < (1ull << 31);
 }
 

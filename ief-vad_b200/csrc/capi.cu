@@ -297,6 +297,12 @@ int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev
                          valid_len_host ? &vr : nullptr);
 }
 
+int iefvad_model_set_pad_dedup(iefvad_model* m, int on) {
+  IEF_CHECK(m, "null model");
+  m->impl.pad_dedup = on != 0;
+  return IEFVAD_OK;
+}
+
 int iefvad_model_set_host_part_rows(iefvad_model* m, int64_t rows) {
   IEF_CHECK(m && rows >= 1, "iefvad_model_set_host_part_rows: need a model and rows >= 1");
   m->host_part_rows = rows;

@@ -237,6 +237,25 @@ inverse_rowmap_kernel(const int* __restrict__ rowmap, long long row_base, long l
     inv[(long long)rowmap[j] - row_base] = int(j);
 }
 
+// one block per chunk item (see ChunkItem / ChunkAux)
+__global__ void __launch_bounds__(kThreads)
+pack_chunks_kernel(const uint4* __restrict__ src, const ChunkItem* __restrict__ items, const ChunkAux* __restrict__ aux,
+                   int D8, uint4* __restrict__ dst) {
+  const ChunkItem it = items[blockIdx.x];
+  const ChunkAux ax = aux[blockIdx.x];
+  const long long n_valid = (long long)it.valid * D8, n_all = (long long)ax.span * D8;
+  const uint4* s = src + ax.src * D8;
+  uint4* d = dst + (long long)it.start * D8;
+  for (long long i = threadIdx.x; i < n_all; i += blockDim.x) d[i] = i < n_valid ? __ldcs(s + i) : make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(kThreads)
+inverse_rowmap_items_kernel(const ChunkItem* __restrict__ items, const ChunkAux* __restrict__ aux, int* __restrict__ inv) {
+  const ChunkItem it = items[blockIdx.x];
+  const ChunkAux ax = aux[blockIdx.x];
+  for (int t = threadIdx.x; t < ax.span; t += blockDim.x) inv[it.start + t] = t < it.valid ? ax.out + t : -1;
+}
+
 // one warp per output row: 16-byte vectors, D % 8 == 0
 __global__ void __launch_bounds__(kThreads)
 gather_rows_kernel(const bf16* __restrict__ ctx, const float* __restrict__ x, const int* __restrict__ rowmap,
@@ -383,6 +402,25 @@ int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long ro
   IEF_CHECK(D % 8 == 0, "gather_rows: D=%d must be a multiple of 8", D);
   if (n_rows == 0) return IEFVAD_OK;
   gather_rows_kernel<<<grid_for(n_rows * 32, num_sms), kThreads, 0, stream>>>(ctx, x, rowmap, row_base, n_rows, D, ctx_c, x_c);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int pack_chunks(const void* src16, const ChunkItem* items, const ChunkAux* aux, int n_items, int D, void* dst16,
+                cudaStream_t stream) {
+  IEF_CHECK(D % 8 == 0, "pack_chunks: D=%d must be a multiple of 8", D);
+  if (n_items == 0) return IEFVAD_OK;
+  pack_chunks_kernel<<<n_items, kThreads, 0, stream>>>(static_cast<const uint4*>(src16), items, aux, D / 8,
+                                                       static_cast<uint4*>(dst16));
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int inverse_rowmap_items(const ChunkItem* items, const ChunkAux* aux, int n_items, int* inv, cudaStream_t stream) {
+  if (n_items == 0) return IEFVAD_OK;
+  inverse_rowmap_items_kernel<<<n_items, kThreads, 0, stream>>>(items, aux, inv);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

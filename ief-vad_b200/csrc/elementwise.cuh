@@ -21,6 +21,17 @@ int layernorm(const float* x, long long M, int D, const float* w1, const float* 
               int hi_fp16 = 0 /* out_hi receives fp16 instead of bf16 (no lo) */,
               const int* f32_row_out = nullptr /* [M]: row of out_f32 that receives source row r, < 0 = none */);
 
+// Packed ("dedup-pad") row layout of a batch of zero-padded chunks: chunk c owns rows [start, start + span) of which the
+// first `valid` hold its real rows, the next one (when the chunk has pads) is ONE zero row standing for all of them,
+// the rest is alignment (zero).  ChunkItem is what the attention kernel reads, ChunkAux what the packers read.
+struct ChunkItem { int start, rows, valid, mult; };            // rows = valid + (mult > 0); mult = T - valid
+struct ChunkAux { long long src; int span; int out; };          // src = first source row, out = first compact row
+// dst[start + t] = src16[src + t] (t < valid), 0 elsewhere in the span; 16-bit rows of D elements
+int pack_chunks(const void* src16, const ChunkItem* items, const ChunkAux* aux, int n_items, int D, void* dst16,
+                cudaStream_t stream);
+// inv[start + t] = out + t (t < valid), -1 elsewhere in the span
+int inverse_rowmap_items(const ChunkItem* items, const ChunkAux* aux, int n_items, int* inv, cudaStream_t stream);
+
 // inv[rowmap[j] - row_base] = j for j < n_rows, every other entry of inv[0, M) = -1
 int inverse_rowmap(const int* rowmap, long long row_base, long long n_rows, long long M, int* inv, int num_sms,
                    cudaStream_t stream);

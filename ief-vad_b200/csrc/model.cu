@@ -1,7 +1,9 @@
 // The IEF-VAD forward (model/imf_vad.py:109-161) as a sequence of sm_100a kernels.
 #include "model.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -290,9 +292,61 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     // valid-rows mode with >= 2 layers: the producers of the last layer's out-projection inputs write compact rows
     // themselves (LayerNorm of layer L-2: fp32 residual; last attention core: context) - no gather pass
     const bool direct_compact = vr && L >= 2;
+    // Pad de-duplication (valid-rows mode, fp16 inputs, fp16 encoder, chunks of <= 256 rows): the zero-pad rows of a
+    // chunk are identical, and stay identical to each other through every row-wise stage and through attention, so
+    // ONE representative per chunk goes through the encoder; as an attention key it counts `mult` times (its score
+    // gets + log mult, which is exactly what mult equal keys contribute to the softmax).  The encoder then works on
+    // Me = sum(valid + 1) packed rows instead of B * T; chunks without valid rows vanish.  Same arithmetic as the
+    // dense forward up to the rounding of that one key's probability.
+    static const bool dedup_off = [] { const char* e = getenv("IEFVAD_DEDUP"); return e && atoi(e) == 0; }();
+    const bool dedup = direct_compact && !fp32_plan && (plan & PLAN_FP16_ATTENTION) && in_dtype == IEFVAD_DT_F16 &&
+                       T <= 256 && T % 32 == 0 && pad_dedup && !dedup_off;
+    long long Me = M;                       // rows the encoder stages before the valid-row cut run on
+    if (dedup) {
+      items_host.clear();
+      aux_host.clear();
+      const bool ragged_src = vr->chunk_start && vr->chunk_valid;
+      long long cur = 0, src = 0, outc = 0;
+      for (long long b = b0; b < b0 + Bs; ++b) {
+        const int n = int(vr->len_host[b]);
+        if (n > 0) {
+          const bool pad = n < T;
+          items_host.push_back({int(cur), n + (pad ? 1 : 0), n, pad ? int(T) - n : 0});
+          aux_host.push_back({ragged_src ? src : (b - b0) * T, 0, int(outc)});
+          cur = (cur + n + (pad ? 1 : 0) + 7) / 8 * 8;
+        }
+        src += n;
+        outc += n;
+      }
+      Me = (cur + 31) / 32 * 32;
+      if (Me < 32) Me = 32;
+      for (size_t i = 0; i < items_host.size(); ++i)
+        aux_host[i].span = int((i + 1 < items_host.size() ? items_host[i + 1].start : Me) - items_host[i].start);
+      // longest chunks first: the persistent attention CTAs take items round-robin, so each gets a similar mix and
+      // the short items (no second query tile) end up together at the end
+      {
+        std::vector<size_t> order(items_host.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return items_host[a].rows > items_host[b].rows; });
+        std::vector<ChunkItem> si(order.size());
+        std::vector<ChunkAux> sa(order.size());
+        for (size_t i = 0; i < order.size(); ++i) { si[i] = items_host[order[i]]; sa[i] = aux_host[order[i]]; }
+        items_host.swap(si);
+        aux_host.swap(sa);
+      }
+      if (!items_host.empty()) {
+        IEF_TRY(items_dev.reserve(items_host.size() * sizeof(ChunkItem)));
+        IEF_TRY(aux_dev.reserve(aux_host.size() * sizeof(ChunkAux)));
+        IEF_CUDA(cudaMemcpyAsync(items_dev.p, items_host.data(), items_host.size() * sizeof(ChunkItem), cudaMemcpyHostToDevice, stream));
+        IEF_CUDA(cudaMemcpyAsync(aux_dev.p, aux_host.data(), aux_host.size() * sizeof(ChunkAux), cudaMemcpyHostToDevice, stream));
+      }
+    }
+    const int n_items = dedup ? int(items_host.size()) : 0;
+    if (dedup && n_items == 0) continue;                 // no valid row in this slab
     if (direct_compact) {
-      IEF_TRY(inv_map.reserve(size_t(M) * sizeof(int)));
-      IEF_TRY(inverse_rowmap(vr->rowmap + out0, vr->row_base + row0, Mo, M, inv_map.as<int>(), num_sms, stream));
+      IEF_TRY(inv_map.reserve(size_t(Me) * sizeof(int)));
+      if (dedup) IEF_TRY(inverse_rowmap_items(items_dev.as<ChunkItem>(), aux_dev.as<ChunkAux>(), n_items, inv_map.as<int>(), stream));
+      else IEF_TRY(inverse_rowmap(vr->rowmap + out0, vr->row_base + row0, Mo, M, inv_map.as<int>(), num_sms, stream));
     }
     for (int m = 0; m < 2; ++m) {
       const bool ragged = vr && vr->chunk_start && vr->chunk_valid;
@@ -303,7 +357,12 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       // residual: no fp32 copy is written, a dense batch is not touched at all before the QKV GEMM
       const bool direct16 = e16 && in_dtype == IEFVAD_DT_F16 && L >= 1 && !(vr && L == 1);
       const bf16* x16 = a_hi.as<bf16>();          // layer-0 operand (and fp16 residual when direct16)
-      if (ragged) {
+      if (dedup) {
+        // dense chunks or ragged packed rows -> the packed layout (the only pass over the inputs)
+        const uint8_t* src = static_cast<const uint8_t*>(inputs[m]) + (ragged ? 0 : size_t(row0) * D * in_esize);
+        IEF_PROF(KC_INGEST, double(Mo) * D * 2 + double(Me) * D * 2,
+                 pack_chunks(src, items_dev.as<ChunkItem>(), aux_dev.as<ChunkAux>(), n_items, D, a_hi.p, stream));
+      } else if (ragged) {
         IEF_CHECK(!esp, "forward: ragged inputs are not combined with the split-encoder plan");
         IEF_PROF(KC_INGEST, double(Mo) * D * in_esize + double(M) * D * (direct16 ? 2 : 4 + 2),
                  ingest_ragged(in, in_dtype, vr->chunk_start + b0, vr->start_base, vr->chunk_valid + b0, Bs, int(T), D,
@@ -334,20 +393,21 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           EpiParams e1;
           e1.hi_fp16 = a16;
           e1.mode = EPI_QKV; e1.bias = ip.b; e1.q = qb.as<bf16>(); e1.k = kb.as<bf16>(); e1.vt = vtb.as<bf16>();
-          e1.T = int(T); e1.H = H; e1.dh = dh; e1.dhp = dhp; e1.Tpad = Tpad; e1.D = D; e1.qscale = qscale;
+          e1.T = dedup ? int(Me) : int(T); e1.H = H; e1.dh = dh; e1.dhp = dhp; e1.Tpad = dedup ? int(Me) : Tpad; e1.D = D; e1.qscale = qscale;
           GemmTcArgs g1;
           g1.A_hi = (i == 0) ? x16 : a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = a16 ? ip.w_h16 : ip.w_hi; g1.W_lo = ip.w_lo;
-          g1.M = int(M); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1; g1.fp16 = a16;
-          IEF_PROF(KC_GEMM_QKV, 6.0 * M * D * D, gemm_tc(g1, e1, num_sms, stream));
+          g1.M = int(Me); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1; g1.fp16 = a16;
+          IEF_PROF(KC_GEMM_QKV, 6.0 * Me * D * D, gemm_tc(g1, e1, num_sms, stream));
           AttnTcArgs at;
           at.q = qb.as<bf16>(); at.k = kb.as<bf16>(); at.vt = vtb.as<bf16>(); at.out = h_hi.as<bf16>(); at.ldo = D;
           at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
+          if (dedup) { at.B = 1; at.T = int(Me); at.Tpad = int(Me); at.items = items_dev.as<int>(); at.n_chunks = n_items; }
           at.fp16 = a16; at.out_fp16 = a16;
           if (direct_compact && last) at.row_out = inv_map.as<int>();
-          IEF_PROF(KC_ATTN_TC, 4.0 * M * T * D, attn_tc(at, stream));
+          IEF_PROF(KC_ATTN_TC, 4.0 * Me * T * D, attn_tc(at, stream));
           // after the last attention core only the valid rows go on: gather (context, residual) into compact matrices
           const bool compact = vr && last;
-          const long long Mc = compact ? Mo : M;
+          const long long Mc = compact ? Mo : Me;
           const bf16* ctx = h_hi.as<bf16>();
           const float* resid = x32.as<float>();
           float* yout = y32.as<float>();

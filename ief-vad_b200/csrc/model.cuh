@@ -70,6 +70,7 @@ struct Model {
   int D = 0, H = 0, L = 0, R = 0, dh = 0, dhp = 0;
   float lambda_ref = 0.5f, factor = 1.f, eps = 1e-8f;
   int plan = PLAN_FP16_HEADS | PLAN_FP16_REFINE | PLAN_FP16_ATTENTION;
+  bool pad_dedup = true;         // valid-rows mode: one representative per chunk for its identical zero-pad rows
   long long max_rows = 262144;   // rows per internal slab (whole batch elements); ~18 KB of workspace per row
   int num_sms = 148;
   int device = 0;
@@ -88,7 +89,9 @@ struct Model {
   DevBuf params_f32, params_hi, params_lo, params_h16;
 
   // workspace (one slab)
-  DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32, inv_map;
+  DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32, inv_map, items_dev, aux_dev;
+  std::vector<ChunkItem> items_host;     // packed-row layout of the current slab (valid-rows mode, see forward)
+  std::vector<ChunkAux> aux_host;
   long long ws_rows = 0;
   int ws_T = 0;
 

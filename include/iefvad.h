@@ -98,6 +98,8 @@ int iefvad_model_forward_host(iefvad_model* m, const void* img_host, const void*
 int iefvad_model_forward_host_to_device(iefvad_model* m, const void* img_host, const void* ev_host, int in_dtype,
                                         int64_t B, int64_t T, float* logits, float* scores, void* stream);
 int iefvad_model_set_host_part_rows(iefvad_model* m, int64_t rows);
+/* Valid-rows mode: compute the identical zero-pad rows of a chunk once (1, default) or row by row (0). */
+int iefvad_model_set_pad_dedup(iefvad_model* m, int on);
 
 /* Evaluation forward: only logits / scores are returned (the seven wide tensors stay in library scratch), from
  * device inputs (inputs_on_host == 0) or through the pipelined host-input path (!= 0).
@@ -106,7 +108,13 @@ int iefvad_model_set_host_part_rows(iefvad_model* m, int64_t rows);
  * attention keys.  valid_len_host: HOST int64 [B]; rowmap: DEVICE int32 [sum len] = b * T + t of every valid row,
  * ascending.  The encoder then runs on all rows up to and including the last attention core; out-projection,
  * LayerNorms, heads, fusion, refinement and classifier (65 %% of the FLOPs) run on the valid rows only, and
- * logits / scores are COMPACT ([sum len]) - bit-identical to the valid rows of the full forward. */
+ * logits / scores are COMPACT ([sum len]).
+ * Pad de-duplication (default on, iefvad_model_set_pad_dedup; fp16 inputs, fp16-operand plans, T <= 256, >= 2
+ * layers): the rows past len are taken to be the all-zero pads process_split writes (data/tools.py:100-114) and are
+ * not read - identical rows stay identical through the encoder, so ONE representative per chunk is computed and
+ * enters every softmax with multiplicity T - len (+ log(T - len) on its score).  Same arithmetic as the dense
+ * forward up to the rounding of that key's probability; with de-duplication off the compact results are
+ * bit-identical to the valid rows of the full forward. */
 int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev, int in_dtype, int inputs_on_host,
                                 int64_t B, int64_t T, const int64_t* valid_len_host, const int32_t* rowmap,
                                 float* logits, float* scores, void* stream);

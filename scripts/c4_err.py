@@ -30,3 +30,12 @@ for wset in ("full_default", "full_perturbed"):
             out = m(img.cuda(), ev.cuda(), None, None, None)["logits"].cpu().numpy().reshape(64, 256)
         e = np.abs(sig(out) - ref) / ref
         print(wset, plan, "valid rows %.2e   pad rows %.2e" % (e[valid].max(), e[~valid].max()), flush=True)
+    # valid-rows mode with pad de-duplication (the evaluation default) against the same golden logits
+    if "HH" in plans:
+        m.temporal.precision = "HH"
+        lens = [int(x) for x in lengths]
+        rowmap = torch.cat([torch.arange(n) + c * 256 for c, n in enumerate(lens)]).to(torch.int32).cuda()
+        with torch.no_grad():
+            out = m.temporal.scores(img.cuda().half(), ev.cuda().half(), None, lens, rowmap)["logits"].cpu().numpy()
+        e = np.abs(sig(out) - ref[valid]) / ref[valid]
+        print(wset, "HH valid-rows + pad de-duplication (fp16 inputs): valid rows %.2e" % e.max(), flush=True)

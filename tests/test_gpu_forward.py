@@ -249,12 +249,14 @@ def test_c5_long_sequence_t16384(pkg, full, plan):
 @pytest.mark.parametrize("plan", ["H", "HH", "B"])
 def test_valid_rows_mode_is_bit_identical_to_the_full_forward(pkg, full, plan):
     """iefvad_model_forward_scores with a row map: stages after the last attention core run on the valid rows only;
-    the compact logits / scores equal the valid rows of the full forward bit for bit (device and host inputs,
-    including an all-zero chunk, a chunk with one valid row and slab / part boundaries)."""
+    without pad de-duplication the compact logits / scores equal the valid rows of the full forward bit for bit
+    (device and host inputs, including an all-zero chunk, a chunk with one valid row and slab / part boundaries);
+    with it (plans with an fp16 encoder) they agree to the rounding of one softmax term."""
     from iefvad_b200 import _lib
     _, synth = pkg
     m, _ = full["full_default"]
     m.temporal.precision = plan
+    _lib.check(_lib.lib.iefvad_model_set_pad_dedup(m.temporal._handle, 0))
     vids = [synth.make_video(40 + i, T) for i, T in enumerate((300, 256, 1, 700, 255))]
     ci = torch.cat([synth.chunk_video(v[0]) for v in vids])                 # [2 + 2 + 1 + 3 + 1, 256, 768]
     ce = torch.cat([synth.chunk_video(v[1]) for v in vids])
@@ -284,5 +286,24 @@ def test_valid_rows_mode_is_bit_identical_to_the_full_forward(pkg, full, plan):
                                            cv.to(torch.int32).cuda())
             torch.cuda.synchronize()
             assert torch.equal(out["scores"], ref_s) and torch.equal(out["logits"], ref_l), ("ragged", part_rows, max_rows)
+        _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, 32768))
+        _lib.check(_lib.lib.iefvad_model_set_max_rows(m.temporal._handle, 262144))
+        # pad de-duplication (the default): one representative per chunk for its zero-pad rows, counted T - len times
+        # in every softmax - the same arithmetic up to the rounding of that key's probability, independent of how the
+        # batch is cut into slabs / parts, and within the plan's tolerance of the reference
+        _lib.check(_lib.lib.iefvad_model_set_pad_dedup(m.temporal._handle, 1))
+        dd = m.temporal.scores(ci.cuda(), ce.cuda(), None, valid, rowmap)
+        rel = ((dd["scores"] - ref_s).abs() / ref_s).max().item()
+        assert rel < (1e-5 if plan == "B" else 3e-4), rel
+        for part_rows, max_rows in ((1024, 262144), (32768, 512), (2048, 768)):
+            _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, part_rows))
+            _lib.check(_lib.lib.iefvad_model_set_max_rows(m.temporal._handle, max_rows))
+            out = m.temporal.scores(ci.pin_memory(), ce.pin_memory(), torch.device("cuda", 0), valid, rowmap)
+            torch.cuda.synchronize()
+            assert torch.equal(out["scores"], dd["scores"]) and torch.equal(out["logits"], dd["logits"]), (part_rows, max_rows)
+            out = m.temporal.scores_ragged(packed_i, packed_e, torch.device("cuda", 0), 256, valid, rowmap, cstart,
+                                           cv.to(torch.int32).cuda())
+            torch.cuda.synchronize()
+            assert torch.equal(out["scores"], dd["scores"]), ("ragged dedup", part_rows, max_rows)
         _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, 32768))
         _lib.check(_lib.lib.iefvad_model_set_max_rows(m.temporal._handle, 262144))

@@ -193,13 +193,21 @@ def test_evaluator_matches_reference_eval_loop(ops):
     with torch.no_grad():
         res3 = ev.step(host_inputs=True)
     assert torch.equal(res3["scores"], res["scores"]) and res3["AUC"] == res["AUC"] and res3["AP"] == res["AP"]
-    # ... and so does the full-rows path (every stage on the pad rows too)
+    # ... the full-rows path (every stage on every pad row) agrees to the rounding of one softmax term: the
+    # valid-rows mode computes the identical zero-pad rows of a chunk once (pad de-duplication) ...
     ev.valid_rows_only = False
     ev.set_device_features(ev.chunk_features(fi), ev.chunk_features(fe))
     with torch.no_grad():
         res4 = ev.step()
-    assert torch.equal(res4["scores"], res["scores"])
+    assert ((res4["scores"] - res["scores"]).abs() / res4["scores"]).max().item() < 3e-4
+    # ... and bit for bit once de-duplication is switched off
+    from iefvad_b200 import _lib
     ev.valid_rows_only = True
+    _lib.check(_lib.lib.iefvad_model_set_pad_dedup(model.temporal._handle, 0))
+    with torch.no_grad():
+        res5 = ev.step()
+    _lib.check(_lib.lib.iefvad_model_set_pad_dedup(model.temporal._handle, 1))
+    assert torch.equal(res4["scores"], res5["scores"])
     # class-wise and Ano-AUC against the oracle on our scores
     st = 0
     by, gby = {}, {}
