@@ -501,10 +501,12 @@ def main():
         "config": {"workload": workload_names[args.workload] + (f" x {world} ranks (one set per rank)" if world > 1 else ""),
                    "videos": int(len(wl["lengths"])), "valid_frames": frames_total,
                    "rows_incl_pad_per_rank": rows_local, "precision_plan": model.temporal.precision,
-                   "pad_rows": ("encoder (through the last attention core) on all rows - the zero-pad rows are attention "
-                                "keys; out-projection, LayerNorms, heads, fusion, refinement, classifier on the valid rows "
-                                "only (the reference's caller drops the pad rows' logits, train/ucf_test.py:112-114); "
-                                "scores bit-identical to the full forward") if evaluator.valid_rows_only
+                   "pad_rows": ("the zero-pad rows of a chunk are identical, so ONE representative per chunk runs through "
+                                "the encoder and counts T - len times as an attention key (softmax multiplicity); "
+                                "out-projection of the last layer, LayerNorms, heads, fusion, refinement, classifier on the "
+                                "valid rows only (the reference's caller drops the pad rows' logits, "
+                                "train/ucf_test.py:112-114); scores within 3e-4 of the row-by-row forward, bit-identical "
+                                "with iefvad_model_set_pad_dedup(0)") if evaluator.valid_rows_only
                                else "every stage on all rows",
                    "l2": "inputs larger than L2 (fp16 chunks %.0f MB per rank)" % (2 * img_c.numel() * 2 / 1e6),
                    "parallelism": f"video-sharded x{world}, one all_gather of scores"},
