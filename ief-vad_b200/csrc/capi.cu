@@ -522,7 +522,7 @@ int iefvad_process_feat(const void* src, int dtype, const int64_t* row_off, int6
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,
                       float* ms_per_iter) {
   IEF_CHECK(M > 0 && M < (1LL << 31) && N > 0 && K > 0 && iters > 0 && ms_per_iter, "iefvad_bench_gemm: bad argument");
-  IEF_CHECK(epi_kind >= 0 && epi_kind <= 6, "iefvad_bench_gemm: epi_kind in [0, 6]");
+  IEF_CHECK(epi_kind >= 0 && epi_kind <= 7, "iefvad_bench_gemm: epi_kind in [0, 7]");
   int sms = 0;
   IEF_TRY(current_sms(&sms));
   cudaStream_t st = nullptr;
@@ -558,6 +558,10 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stage
   if (epi_kind == 6) {
     ep.resid = (float*)resid; ep.ld_resid = N; ep.alpha = -0.5f; ep.out_f32 = (float*)of; ep.ld_f32 = N;
     ep.out_hi = (bf16*)oh; ep.ld_bf = N; ep.hi_fp16 = 1;
+  }
+  if (epi_kind == 7) {        // refinement Linear2 of the fp16 plans: fp16 pair in, fp16 pair out (in place)
+    ep.resid_h16 = oh; ep.resid_l16 = ol; ep.ld_resid = N; ep.alpha = -0.5f;
+    ep.out_hi = (bf16*)oh; ep.out_lo = (bf16*)ol; ep.ld_bf = N; ep.hi_fp16 = 1;
   }
   if (epi_kind == 4) {
     IEF_CHECK(N % (3 * H * 32) == 0 && M % T == 0, "iefvad_bench_gemm: qkv epilogue needs N = 3*8*dh, M %% 256 == 0");

@@ -260,7 +260,8 @@ int iefvad_process_feat(const void* src, int dtype, const int64_t* row_off, int6
 /* Micro-benchmark of the tcgen05 GEMM on library-allocated buffers (synchronises; default stream): M x N x K,
  * nsplit 1 | 3, tile_n 0 | 64 | 128 | 256 | 512 (as for iefvad_linear), stages 0 (= as many as fit) or a cap on the operand ring depth, epi_kind 0 = mainloop only (discard), 1 = fp32 out, 2 = refinement
  * epilogue (fp32 residual in, fp32 + bf16 hi/lo out), 3 = ReLU -> bf16 hi/lo, 4 = QKV scatter, 5 = fp16 operands,
- * ReLU -> fp16, 6 = fp16 operands, fp32 residual in, fp32 + fp16 out (the two refinement Linears of plan H).  Writes the mean
+ * ReLU -> fp16, 6 = fp16 operands, fp32 residual in, fp32 + fp16 out, 7 = fp16 operands, fp16 hi + lo pair residual in, fp16 pair out in
+ * place (5 and 7 = the two refinement Linears of the default plan).  Writes the mean
  * device time of `iters` back-to-back launches (CUDA events). */
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,
                       float* ms_per_iter);
