@@ -43,7 +43,7 @@ int current_sms(int* out) {
 struct Scratch {   // stream-ordered temporaries of the stand-alone operators (test surface, not the hot path)
   cudaStream_t s;
   std::vector<void*> ptrs;
-  explicit Scratch(cudaStream_t st) : s(st) {}
+  explicit Scratch(cudaStream_t st) : s(st) { keep_async_pool(); }
   ~Scratch() {
     for (void* p : ptrs) cudaFreeAsync(p, s);
   }

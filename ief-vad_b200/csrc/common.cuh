@@ -16,6 +16,7 @@ namespace iefvad {
 enum : int { IEFVAD_OK = 0, IEFVAD_ERR_INVALID = 1, IEFVAD_ERR_CUDA = 2, IEFVAD_ERR_STATE = 3 };
 
 void set_error(const char* fmt, ...);
+void keep_async_pool();              // once per device: the stream-ordered allocator keeps freed blocks (no OS round trips)
 void count_launches(int n);          // kernels launched by this library (bench.py's gpu_launches)
 unsigned long long launch_count();
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);

@@ -19,7 +19,7 @@ namespace {
 struct Scratch {   // stream-ordered temporaries
   cudaStream_t s;
   std::vector<void*> ptrs;
-  explicit Scratch(cudaStream_t st) : s(st) {}
+  explicit Scratch(cudaStream_t st) : s(st) { keep_async_pool(); }
   ~Scratch() {
     for (void* p : ptrs) cudaFreeAsync(p, s);
   }

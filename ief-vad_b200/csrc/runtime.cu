@@ -13,6 +13,20 @@
 
 namespace iefvad {
 
+// cudaMallocAsync's default pool hands memory back to the OS at every synchronisation point (release threshold 0):
+// an operator that takes gigabytes of scratch (a T = 16384 adjacency) then spends tens of ms per call in the driver.
+void keep_async_pool() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 static thread_local char g_err[1024] = "";
 
 void set_error(const char* fmt, ...) {
