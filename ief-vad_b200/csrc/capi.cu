@@ -146,13 +146,13 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
     const bool ragged_in = chunk_start_dev != nullptr;
     double growth = env_growth > 1.0 ? env_growth : (ragged_in ? 3.0 : 1.4);
     double want = env_first > 0.0 ? env_first : double(m->host_part_rows) / (ragged_in ? 8.0 : 4.0);
-    // Back-to-back calls: the previous call's last part is still computing, so this call's first copy hides behind
-    // it whatever its size - two halves then keep the GEMM grids full (a small first part only pays when the device
-    // is idle at the call).
+    // Back-to-back calls: the previous call's last part is still computing, so this call's copy hides behind it
+    // whatever its size - the whole batch then travels as ONE part into the other input buffer (full GEMM grids; a
+    // small first part only pays when the device is idle at the call).
     if (env_first <= 0.0 && m->host_seq > 0 && m->ev_consumed[(m->host_seq - 1) & 1] &&
         cudaEventQuery(m->ev_consumed[(m->host_seq - 1) & 1]) == cudaErrorNotReady) {
       (void)cudaGetLastError();            // cudaErrorNotReady is a status, not a failure: keep it out of the next check
-      want = double(((B + 1) / 2) * T);
+      want = double(B * T);
       growth = 1.0;
     }
     int64_t left = B;
