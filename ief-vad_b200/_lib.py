@@ -38,6 +38,7 @@ _SIGS = {
     "iefvad_model_forward_host_to_device": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
     "iefvad_model_set_host_part_rows": (_i, [_vp, _i64]),
     "iefvad_model_set_pad_dedup": (_i, [_vp, _i]),
+    "iefvad_event_image": (_i, [_vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
     "iefvad_model_forward_scores_ragged": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "iefvad_model_forward_scores": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "iefvad_fuse": (_i, [_vp] * 4 + [_i64, _f, _f] + [_vp] * 3 + [_vp]),

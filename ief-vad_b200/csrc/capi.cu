@@ -9,6 +9,7 @@
 
 #include "attention.cuh"
 #include "elementwise.cuh"
+#include "event.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
 #include "model.cuh"
@@ -517,6 +518,22 @@ int iefvad_process_feat(const void* src, int dtype, const int64_t* row_off, int6
   IEF_CHECK(dtype >= 0 && dtype <= 2, "unsupported dtype code %d", dtype);
   return process_feat(src, dtype, reinterpret_cast<const long long*>(row_off), V, D, length, dst,
                       reinterpret_cast<long long*>(out_len), nan_to_num, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_event_image(const uint8_t* frames, int64_t B, int C, int H, int W, float threshold, float clamp_max,
+                       float* sum_out, float* event_out, void* stream) {
+  IEF_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1, "iefvad_event_image: bad shape");
+  if (B == 0) return IEFVAD_OK;
+  IEF_CHECK(frames, "iefvad_event_image: null frames");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  Scratch sc(st);
+  void *cnt, *mx;
+  IEF_TRY(sc.get(&cnt, size_t(B) * H * W * 4));
+  IEF_TRY(sc.get(&mx, 16));
+  return event_image(frames, B, C, H, W, threshold, clamp_max, sum_out, event_out, static_cast<float*>(cnt),
+                     static_cast<unsigned*>(mx), sms, st);
 }
 
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,

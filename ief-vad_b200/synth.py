@@ -122,3 +122,37 @@ def make_c4_batch(B: int = 64, T: int = 256, seed: int = 4, num_class: int = 14)
     labels[: B // 2, 0] = 1.0
     labels[B // 2:, 1 + (torch.arange(B - B // 2) % (num_class - 1))] = 1.0
     return img, ev, torch.from_numpy(lengths.astype(np.int64)), labels
+
+
+def make_event_frames(name: str) -> np.ndarray:
+    """Seeded uint8 frame stacks [B, 16, 224, 224, 3] for the event-synthesis row (extracting/ucf_gen_event.py:85-91):
+    `rand` = independent noise, `smooth` = a fixed picture plus sigma-14 noise (frame differences straddle the
+    thresholds 10 / 25 the extraction scripts use), `static` = constant frames (no event anywhere: 0 / 0 = NaN)."""
+    rng = np.random.default_rng({"rand": 21, "smooth": 22, "static": 23, "ties": 24}[name])
+    if name == "rand":
+        return rng.integers(0, 256, (2, 16, 224, 224, 3), dtype=np.uint8)
+    if name == "smooth":
+        base = rng.integers(0, 256, (2, 1, 224, 224, 3))
+        return np.clip(base + rng.normal(0, 14, (2, 16, 224, 224, 3)), 0, 255).astype(np.uint8)
+    if name == "static":
+        return np.full((1, 16, 224, 224, 3), 77, dtype=np.uint8)
+    if name == "ties":
+        # every pixel pair whose exact gray difference lies within 4e-5 of the thresholds 25 / 10 (integer channel
+        # differences a, b, c with 0.2989 a + 0.587 b + 0.114 c ~ threshold): the comparison `diff > threshold` is then
+        # decided by the last bit of the fp32 evaluation order - these cases pin that order.  [1, 2, 1, N, 3]
+        rows = []
+        for thr in (25.0, 10.0):
+            for a in range(-255, 256):
+                for b in range(-255, 256):
+                    c = (thr - 0.2989 * a - 0.587 * b) / 0.114
+                    for cc in (int(np.floor(c)), int(np.ceil(c))):
+                        if -255 <= cc <= 255 and abs(0.2989 * a + 0.587 * b + 0.114 * cc - thr) < 4e-5:
+                            for base in range(0, 256, 17):
+                                p1 = (base + a, base + b, base + cc)
+                                if all(0 <= x <= 255 for x in p1):
+                                    rows.append(((base, base, base), p1))
+        rows = rows[: len(rows) // 4 * 4]
+        f0 = np.array([r[0] for r in rows], dtype=np.uint8)
+        f1 = np.array([r[1] for r in rows], dtype=np.uint8)
+        return np.stack([f0, f1], 0)[None, :, None, :, :].copy()
+    raise KeyError(name)

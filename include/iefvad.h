@@ -253,6 +253,15 @@ int iefvad_process_split(const void* src, int dtype, const int64_t* row_off, int
 int iefvad_process_feat(const void* src, int dtype, const int64_t* row_off, int64_t V, int D, int length, float* dst,
                         int64_t* out_len, int nan_to_num, void* stream);
 
+/* Synthetic event frames (row N4), extracting/ucf_gen_event.py: generate_event_image (:21-37) and the clamp / normalise /
+ * stack lines of its caller (:91-95).  frames: DEVICE uint8 [B, C, H, W, 3] (C decoded frames per stack, 16 in the
+ * reference).  sum_out (DEVICE fp32 [B, H, W], may be NULL) = number of the C - 1 frame-to-frame differences of the
+ * gray image 0.2989 R + 0.5870 G + 0.1140 B whose magnitude exceeds `threshold` (what generate_event_image returns);
+ * event_out (DEVICE fp32 [B, 3, H, W], may be NULL) = clamp(sum, 0, clamp_max) / max over the whole batch, the same
+ * plane in all three channels (an event-free batch gives 0 / 0 = NaN, as in the reference). */
+int iefvad_event_image(const uint8_t* frames, int64_t B, int C, int H, int W, float threshold, float clamp_max,
+                       float* sum_out, float* event_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Instrumentation used by bench.py
  * ---------------------------------------------------------------------------------------------- */

@@ -468,6 +468,45 @@ def transformer(x: np.ndarray, blocks: List[Dict[str, np.ndarray]], heads: int,
 
 
 # --------------------------------------------------------------------------
+# synthetic event frames (row N4): extracting/ucf_gen_event.py
+# --------------------------------------------------------------------------
+
+def _r32(x):
+    return np.asarray(x, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+
+def gray_image(frames: np.ndarray) -> np.ndarray:
+    """extracting/ucf_gen_event.py:22-33: torch.tensordot(frames.float(), [0.2989, 0.5870, 0.1140]) on the CPU.
+    The contraction is an MKL sgemv with K = 3; its rounding is fl(fma(G, w1, fl(R w0)) + fl(B w2)) (found by
+    comparing every fused / unfused association order with torch on 2e5 random pixels, pinned by the threshold-tie
+    cases of tests/golden/event.npz).  float64 holds every float32 product and two-term sum exactly, so rounding a
+    float64 result to float32 reproduces both the plain and the fused float32 operations."""
+    w = np.array([0.2989, 0.5870, 0.1140], dtype=np.float32).astype(np.float64)
+    f = np.asarray(frames).astype(np.float64)
+    t = _r32(f[..., 0] * w[0])
+    t = _r32(f[..., 1] * w[1] + t)                    # fma: one rounding
+    u = _r32(f[..., 2] * w[2])
+    return _r32(t + u).astype(np.float32)
+
+
+def generate_event_image(frames: np.ndarray, threshold=25) -> np.ndarray:
+    """extracting/ucf_gen_event.py:21-37.  frames uint8 [B, C, H, W, 3] -> [B, H, W] float32 event counts."""
+    g = gray_image(frames)
+    diffs = np.abs(g[:, 1:] - g[:, :-1])              # float32 subtraction (:34)
+    return (diffs > np.float32(threshold)).astype(np.float32).sum(1)            # :36-37
+
+
+def event_images(frames: np.ndarray, threshold=25, clamp=10) -> np.ndarray:
+    """The caller's lines extracting/ucf_gen_event.py:91-95: clamp, divide by the batch maximum, stack 3 channels
+    (an event-free batch divides 0 by 0 = NaN there too)."""
+    event = np.clip(generate_event_image(frames, threshold), np.float32(0), np.float32(clamp))
+    if event.size != 0:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            event = (event / event.max()).astype(np.float32)
+    return np.stack([event, event, event], 1)
+
+
+# --------------------------------------------------------------------------
 # Error metrics (SURVEY.md section 8c "metric definition")
 # --------------------------------------------------------------------------
 

@@ -311,8 +311,36 @@ def tools_cases():
     save("tools.npz", **arrays)
 
 
+def event_cases():
+    """extracting/ucf_gen_event.py: `generate_event_image` (:21-37) run as-is plus the clamp / normalise / stack lines of
+    its caller (:91-95, transcribed below with their line numbers).  The module itself imports cv2 / clip / matplotlib
+    at the top, none of which is installed, so only the function's own source is executed (ast-extracted, unmodified)."""
+    import ast
+    path = os.path.join(REF, "extracting", "ucf_gen_event.py")
+    src = open(path).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "generate_event_image")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    generate_event_image = ns["generate_event_image"]
+    import hashlib
+    arrays = {}
+    for name in ("rand", "smooth", "static", "ties"):
+        frames = synth.make_event_frames(name)
+        arrays[f"{name}:sha256"] = np.array(hashlib.sha256(frames.tobytes()).hexdigest())
+        for thr, clamp in ((25, 10), (10, 10), (25, 3)):
+            event = generate_event_image(frames, thr)                 # :91  [B, H, W] counts
+            arrays[f"{name}:{thr}:sum"] = event.numpy().astype(np.uint8)          # counts <= 15
+            assert np.array_equal(arrays[f"{name}:{thr}:sum"].astype(np.float32), event.numpy())
+            event = torch.clamp(event, 0, clamp)                      # :92
+            if event.numel() != 0:
+                event = event / event.max()                           # :93-94
+            event = torch.stack([event, event, event], 1)             # :95
+            arrays[f"{name}:{thr}:{clamp}:event"] = event.numpy()[:, 0].copy()    # the three channels are one tensor
+    save("event.npz", **arrays)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["small", "full", "clas2", "eval", "sklearn", "layers", "tools"]
+    which = sys.argv[1:] or ["small", "full", "clas2", "eval", "sklearn", "layers", "tools", "event"]
     with torch.no_grad():
         if "small" in which:
             small_models()
@@ -328,3 +356,5 @@ if __name__ == "__main__":
             layer_cases()
         if "tools" in which:
             tools_cases()
+        if "event" in which:
+            event_cases()

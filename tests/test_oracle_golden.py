@@ -135,3 +135,20 @@ def test_input_shaping_restatement_matches_reference_tools():
             pf, m = O.process_feat(feat, 256)
             assert m == int(z[f"{dt_name}:{t}:feat_len"])
             assert np.array_equal(np.asarray(pf, dtype=np.float32), np.asarray(z[f"{dt_name}:{t}:feat"], dtype=np.float32))
+
+
+@pytest.mark.parametrize("name", ["rand", "smooth", "static", "ties"])
+def test_event_synthesis_restatement_matches_reference(name):
+    """Row N4: extracting/ucf_gen_event.py:21-37,91-95 run as-is (golden) vs the oracle - counts bit-exact, including
+    the pixel pairs whose gray difference sits on a threshold (decided by the fp32 evaluation order)."""
+    import hashlib
+    from iefvad_b200.synth import make_event_frames
+    z = load_golden("event.npz")
+    frames = make_event_frames(name)
+    assert hashlib.sha256(frames.tobytes()).hexdigest() == str(z[f"{name}:sha256"])
+    for thr, clamp in ((25, 10), (10, 10), (25, 3)):
+        assert np.array_equal(O.generate_event_image(frames, thr), z[f"{name}:{thr}:sum"].astype(np.float32))
+        ev = O.event_images(frames, thr, clamp)
+        assert ev.shape == (frames.shape[0], 3) + frames.shape[2:4]
+        for c in range(3):
+            assert np.array_equal(ev[:, c], z[f"{name}:{thr}:{clamp}:event"], equal_nan=True)
