@@ -416,6 +416,7 @@ int attn_tc(const AttnTcArgs& a, cudaStream_t stream) {
   IEF_CHECK(a.Tpad % 8 == 0 && a.Tpad >= a.T, "attn_tc: Tpad=%d must be a multiple of 8 and >= T=%d", a.Tpad, a.T);
   IEF_CHECK(a.ldo % 8 == 0, "attn_tc: ldo must be a multiple of 8");
   if (attn_short_supported(a)) return attn_short(a, stream);
+  if (attn_long_supported(a)) return attn_long(a, stream);
   IEF_CHECK(a.B <= 65535 && a.H <= 65535, "attn_tc: B=%d / H=%d exceed the grid limits", a.B, a.H);
   static const int env_kb = [] { const char* e = getenv("IEFVAD_ATTN_KB"); return e ? atoi(e) : 0; }();   // tuning knob
   const int kb = a.key_block ? a.key_block : (env_kb ? env_kb : 64);      // two CTAs per SM measured faster at every T (7.75 vs 7.95 ms on config 5)

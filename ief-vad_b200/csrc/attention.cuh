@@ -26,6 +26,10 @@ int attn_tc(const AttnTcArgs& a, cudaStream_t stream);
 
 // T <= 256 without masks (every chunk the reference's callers produce): persistent kernel, P kept in TMEM
 // (attention_short.cu).  attn_tc dispatches here when attn_short_supported(a); IEFVAD_ATTN_SHORT=0 disables it.
+// T > 256 without masks: persistent two-tile kernel, single-pass softmax with integer (power-of-two) maxima, O
+// accumulated in TMEM (attention_long.cu); IEFVAD_ATTN_LONG=0 falls back to the flash-style attn_tc_kernel.
+bool attn_long_supported(const AttnTcArgs& a);
+int attn_long(const AttnTcArgs& a, cudaStream_t stream);
 bool attn_short_supported(const AttnTcArgs& a);
 int attn_short(const AttnTcArgs& a, cudaStream_t stream);
 
