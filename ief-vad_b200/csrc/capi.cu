@@ -178,7 +178,10 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
   }
   int64_t maxB = 0;
   for (int64_t pb : partsB) maxB = pb > maxB ? pb : maxB;
-  const size_t rows = size_t(maxB) * T;
+  // the input buffers are sized for the one-part schedule of back-to-back calls from the start: growing them later
+  // would put a cudaFree / cudaMalloc (a device-wide synchronisation) into the middle of a pipelined loop
+  const int64_t fullB = (B * T <= cap_rows) ? B : maxB;
+  const size_t rows = size_t(fullB > maxB ? fullB : maxB) * T;
   if (!m->copy_stream) {
     IEF_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
