@@ -53,7 +53,7 @@ template <int DH, int DHP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ out, int ldo, int T, int H, int n_items,
-                 int fp16, int out_fp16) {
+                 int fp16, int out_fp16, const int* __restrict__ row_out) {
   using Cfg = LongCfg<DH, DHP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -295,8 +295,10 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       *slot(parx, hf) = l;
       named_bar_sync(1 + t, 256);
       const float inv = 1.f / (l + *slot(parx, hf ^ 1));
-      if (tq < T) {
-        bf16* dst = out + ((long long)b * T + tq) * ldo + h * DH + hf * (DH / 2);
+      long long ro = (long long)b * T + (tq < T ? tq : 0);
+      if (row_out) ro = __ldg(row_out + ro);              // compact layouts: < 0 = this row is dropped
+      if (tq < T && ro >= 0) {
+        bf16* dst = out + ro * ldo + h * DH + hf * (DH / 2);
 #pragma unroll
         for (int d = 0; d < DH / 2; d += 8) {
           uint4 u;
@@ -337,7 +339,7 @@ int launch_attn_long(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
   IEF_CHECK(items < (1LL << 31), "attn_long: too many work items");
   const int grid = items < num_sms ? int(items) : num_sms;
   attn_long_kernel<DH, DHP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, a.out, a.ldo, a.T, a.H, int(items),
-                                                                        a.fp16, a.out_fp16);
+                                                                        a.fp16, a.out_fp16, a.row_out);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;
@@ -347,7 +349,7 @@ int launch_attn_long(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
 
 bool attn_long_supported(const AttnTcArgs& a) {
   static const int env_off = [] { const char* e = getenv("IEFVAD_ATTN_LONG"); return (e && atoi(e) == 0) ? 1 : 0; }();
-  return !env_off && a.T > 256 && !a.attn_mask && !a.key_pad && !a.items && !a.row_out;
+  return !env_off && a.T > 256 && !a.attn_mask && !a.key_pad && !a.items;
 }
 
 int attn_long(const AttnTcArgs& a, cudaStream_t stream) {

@@ -307,3 +307,31 @@ def test_valid_rows_mode_is_bit_identical_to_the_full_forward(pkg, full, plan):
             assert torch.equal(out["scores"], dd["scores"]), ("ragged dedup", part_rows, max_rows)
         _lib.check(_lib.lib.iefvad_model_set_host_part_rows(m.temporal._handle, 32768))
         _lib.check(_lib.lib.iefvad_model_set_max_rows(m.temporal._handle, 262144))
+
+
+@pytest.mark.parametrize("T", [64, 160, 512])
+def test_valid_rows_mode_other_chunk_lengths(pkg, full, T):
+    """The valid-rows forward is not tied to 256-row chunks: T = 64 / 160 take the pad-de-duplicated path (T <= 256,
+    T % 32 == 0: within the rounding of one softmax term of the row-by-row forward), T = 512 the row-by-row path with
+    the flash-style attention kernel writing compact rows (bit-identical)."""
+    _, synth = pkg
+    m, _ = full["full_default"]
+    m.temporal.precision = "HH"
+    rng = np.random.default_rng(T)
+    valid = [T, 0, 1, T - 1, int(rng.integers(2, T - 1)), T, int(rng.integers(2, T - 1))]
+    B = len(valid)
+    img = torch.zeros(B, T, 768, dtype=torch.float16)
+    ev = torch.zeros(B, T, 768, dtype=torch.float16)
+    for b, n in enumerate(valid):
+        a, e = synth.make_video(900 + 10 * b + T, max(n, 1))
+        img[b, :n], ev[b, :n] = a[:n], e[:n]
+    rowmap = torch.cat([torch.arange(n) + c * T for c, n in enumerate(valid)]).to(torch.int32).cuda()
+    with torch.no_grad():
+        ref = m.temporal(img.cuda(), ev.cuda(), with_scores=True)
+        ref_s = ref["scores"].reshape(-1)[rowmap.long()]
+        out = m.temporal.scores(img.cuda(), ev.cuda(), None, valid, rowmap)
+    assert out["scores"].shape == ref_s.shape
+    if T > 256:
+        assert torch.equal(out["scores"], ref_s)
+    else:
+        assert ((out["scores"] - ref_s).abs() / ref_s).max().item() < 3e-4
