@@ -246,7 +246,9 @@ pack_chunks_kernel(const uint4* __restrict__ src, const ChunkItem* __restrict__ 
   const long long n_valid = (long long)it.valid * D8, n_all = (long long)ax.span * D8;
   const uint4* s = src + ax.src * D8;
   uint4* d = dst + (long long)it.start * D8;
-  for (long long i = threadIdx.x; i < n_all; i += blockDim.x) d[i] = i < n_valid ? __ldcs(s + i) : make_uint4(0, 0, 0, 0);
+  // gridDim.y blocks share a chunk (a chunk is at most 256 rows: one block per chunk leaves most SMs with too little in flight)
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n_all; i += (long long)gridDim.y * blockDim.x)
+    d[i] = i < n_valid ? __ldcs(s + i) : make_uint4(0, 0, 0, 0);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -411,7 +413,7 @@ int pack_chunks(const void* src16, const ChunkItem* items, const ChunkAux* aux, 
                 cudaStream_t stream) {
   IEF_CHECK(D % 8 == 0, "pack_chunks: D=%d must be a multiple of 8", D);
   if (n_items == 0) return IEFVAD_OK;
-  pack_chunks_kernel<<<n_items, kThreads, 0, stream>>>(static_cast<const uint4*>(src16), items, aux, D / 8,
+  pack_chunks_kernel<<<dim3(n_items, 8), kThreads, 0, stream>>>(static_cast<const uint4*>(src16), items, aux, D / 8,
                                                        static_cast<uint4*>(dst16));
   count_launches(1);
   IEF_CUDA(cudaGetLastError());

@@ -36,6 +36,8 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         self.epsilon = epsilon
         self.dropout = dropout          # attention dropout only acts in train(); this path is forward-only (eval)
         self.precision = os.environ.get("IEFVAD_PLAN", "HH")
+        # valid-rows evaluation forward: compute the identical zero-pad rows of a chunk once (pad de-duplication)
+        self.pad_dedup = True
 
         # nn.MultiheadAttention / LayerNorm / Linear instances are used purely as parameter containers: they give
         # the reference's state_dict keys and consume the RNG exactly like the reference constructor does
@@ -141,6 +143,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             h = self._native(device)
             self._sync_params(h, device, stream)
             _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
+            _lib.check(_lib.lib.iefvad_model_set_pad_dedup(h, 1 if self.pad_dedup else 0))
             wide = torch.empty((7, B, T, D), dtype=torch.float32, device=device)
             logits = torch.empty((B, T, 1), dtype=torch.float32, device=device)
             scores = torch.empty((B, T), dtype=torch.float32, device=device) if with_scores else None
@@ -198,6 +201,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             h = self._native(device)
             self._sync_params(h, device, stream)
             _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
+            _lib.check(_lib.lib.iefvad_model_set_pad_dedup(h, 1 if self.pad_dedup else 0))
             logits = torch.empty(max(n_out, 1), dtype=torch.float32, device=device)[:n_out]
             scores = torch.empty(max(n_out, 1), dtype=torch.float32, device=device)[:n_out]
             _lib.check(_lib.lib.iefvad_model_forward_scores(
@@ -237,6 +241,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             h = self._native(device)
             self._sync_params(h, device, stream)
             _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
+            _lib.check(_lib.lib.iefvad_model_set_pad_dedup(h, 1 if self.pad_dedup else 0))
             logits = torch.empty(max(n, 1), dtype=torch.float32, device=device)[:n]
             scores = torch.empty(max(n, 1), dtype=torch.float32, device=device)[:n]
             _lib.check(_lib.lib.iefvad_model_forward_scores_ragged(

@@ -256,7 +256,7 @@ def test_valid_rows_mode_is_bit_identical_to_the_full_forward(pkg, full, plan):
     _, synth = pkg
     m, _ = full["full_default"]
     m.temporal.precision = plan
-    _lib.check(_lib.lib.iefvad_model_set_pad_dedup(m.temporal._handle, 0))
+    m.temporal.pad_dedup = False
     vids = [synth.make_video(40 + i, T) for i, T in enumerate((300, 256, 1, 700, 255))]
     ci = torch.cat([synth.chunk_video(v[0]) for v in vids])                 # [2 + 2 + 1 + 3 + 1, 256, 768]
     ce = torch.cat([synth.chunk_video(v[1]) for v in vids])
@@ -291,7 +291,7 @@ def test_valid_rows_mode_is_bit_identical_to_the_full_forward(pkg, full, plan):
         # pad de-duplication (the default): one representative per chunk for its zero-pad rows, counted T - len times
         # in every softmax - the same arithmetic up to the rounding of that key's probability, independent of how the
         # batch is cut into slabs / parts, and within the plan's tolerance of the reference
-        _lib.check(_lib.lib.iefvad_model_set_pad_dedup(m.temporal._handle, 1))
+        m.temporal.pad_dedup = True
         dd = m.temporal.scores(ci.cuda(), ce.cuda(), None, valid, rowmap)
         rel = ((dd["scores"] - ref_s).abs() / ref_s).max().item()
         assert rel < (1e-5 if plan == "B" else 3e-4), rel

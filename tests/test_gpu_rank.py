@@ -203,10 +203,10 @@ def test_evaluator_matches_reference_eval_loop(ops):
     # ... and bit for bit once de-duplication is switched off
     from iefvad_b200 import _lib
     ev.valid_rows_only = True
-    _lib.check(_lib.lib.iefvad_model_set_pad_dedup(model.temporal._handle, 0))
+    model.temporal.pad_dedup = False
     with torch.no_grad():
         res5 = ev.step()
-    _lib.check(_lib.lib.iefvad_model_set_pad_dedup(model.temporal._handle, 1))
+    model.temporal.pad_dedup = True
     assert torch.equal(res4["scores"], res5["scores"])
     # class-wise and Ano-AUC against the oracle on our scores
     st = 0
