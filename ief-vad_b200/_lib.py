@@ -61,6 +61,8 @@ _SIGS = {
     "iefvad_process_feat": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _i, _vp]),
     "iefvad_bench_gemm": (_i, [_i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "iefvad_launch_count": (C.c_uint64, []),
+    "iefvad_alloc_generation": (C.c_uint64, []),
+    "iefvad_add_launches": (None, [C.c_uint64]),
     "iefvad_profile_enable": (_i, [_i]),
     "iefvad_profile_read": (_i, [_vp, _vp, _vp]),
 }

@@ -614,6 +614,8 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stage
 }
 
 uint64_t iefvad_launch_count(void) { return launch_count(); }
+uint64_t iefvad_alloc_generation(void) { return alloc_generation(); }
+void iefvad_add_launches(uint64_t n) { count_launches(int(n)); }
 
 int iefvad_profile_enable(int on) {
   profiler().on = on != 0;

@@ -9,8 +9,12 @@
 
 namespace iefvad {
 
+static unsigned long long g_alloc_generation = 0;
+unsigned long long alloc_generation() { return g_alloc_generation; }
+
 int DevBuf::reserve(size_t need) {
   if (need <= bytes) return IEFVAD_OK;
+  ++g_alloc_generation;            // every address handed out before may be gone: captured CUDA graphs are stale
   if (p) {
     IEF_CUDA(cudaFree(p));
     p = nullptr;

@@ -54,6 +54,8 @@ struct ParamSlot {
 // attention core; everything after it (out-projection, LayerNorms, heads, fusion, refinement, classifier - 65 % of
 // the FLOPs) runs on the valid rows only, gathered into a compact matrix.  Every output is then COMPACT
 // ([sum len, ...], valid row j of the whole call at index j) and bit-identical to the valid rows of the full forward.
+unsigned long long alloc_generation();   // bumped whenever a library workspace is (re)allocated
+
 struct ValidRows {
   const long long* len_host = nullptr;  // HOST [B]: valid rows (a prefix) of each batch element, 0 <= len <= T
   const int* rowmap = nullptr;          // DEVICE [sum len]: row index (b * T + t, relative to this call's first row,

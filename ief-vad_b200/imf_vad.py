@@ -66,6 +66,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
 
     # ------------------------------------------------------------------ native model management
     def _release(self):
+        self.__dict__.pop("_graphs", None)       # captured graphs hold addresses of the handle's workspaces
         if getattr(self, "_handle", None):
             _lib.lib.iefvad_model_destroy(self._handle)
         self._handle = None
@@ -144,13 +145,24 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             self._sync_params(h, device, stream)
             _lib.check(_lib.lib.iefvad_model_set_plan(h, plan))
             _lib.check(_lib.lib.iefvad_model_set_pad_dedup(h, 1 if self.pad_dedup else 0))
-            wide = torch.empty((7, B, T, D), dtype=torch.float32, device=device)
-            logits = torch.empty((B, T, 1), dtype=torch.float32, device=device)
-            scores = torch.empty((B, T), dtype=torch.float32, device=device) if with_scores else None
-            _lib.check(_lib.lib.iefvad_model_forward(
-                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], B, T,
-                wide[0].data_ptr(), logits.data_ptr(), wide[1].data_ptr(), wide[2].data_ptr(), wide[3].data_ptr(),
-                wide[4].data_ptr(), wide[5].data_ptr(), wide[6].data_ptr(), _lib.ptr(scores), stream))
+
+            def launch(img_t, ev_t, wide_t, logits_t, scores_t):
+                _lib.check(_lib.lib.iefvad_model_forward(
+                    h, img_t.data_ptr(), ev_t.data_ptr(), codes[img_t.dtype], B, T,
+                    wide_t[0].data_ptr(), logits_t.data_ptr(), wide_t[1].data_ptr(), wide_t[2].data_ptr(),
+                    wide_t[3].data_ptr(), wide_t[4].data_ptr(), wide_t[5].data_ptr(), wide_t[6].data_ptr(),
+                    _lib.ptr(scores_t), torch.cuda.current_stream(device).cuda_stream))
+
+            # Small problems are bound by launching ~60 kernels from the host (0.5 ms for one 256-row clip): replay
+            # them as one CUDA graph over static buffers (two copies in, one clone out).  IEFVAD_GRAPH_ROWS=0 disables.
+            replay = self._graph_replay(device, B, T, D, img, ev, plan, with_scores, launch) if B * T else None
+            if replay is not None:
+                wide, logits, scores = replay
+            else:
+                wide = torch.empty((7, B, T, D), dtype=torch.float32, device=device)
+                logits = torch.empty((B, T, 1), dtype=torch.float32, device=device)
+                scores = torch.empty((B, T), dtype=torch.float32, device=device) if with_scores else None
+                launch(img, ev, wide, logits, scores)
         out = {
             "fused": wide[0], "logits": logits, "image_mu": wide[1], "event_mu": wide[2],
             "image_logvar": wide[3], "event_logvar": wide[4], "w_i": wide[5], "w_e": wide[6],
@@ -159,6 +171,56 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             out["scores"] = scores
         return out
 
+
+    def _graph_replay(self, device, B, T, D, img, ev, plan, with_scores, launch):
+        """One CUDA-graph replay of the forward for a small [B, T] problem, or None (too large, disabled, already
+        capturing, or capture failed once for this shape).  The graph is captured over static input / output buffers
+        after an eager warm-up call that sizes every library workspace; parameters live in the library's own arena, so
+        a `load_state_dict` / optimizer step between calls is picked up by the replay."""
+        limit = int(os.environ.get("IEFVAD_GRAPH_ROWS", "2048") or 0)
+        if B * T > limit or torch.cuda.is_current_stream_capturing():
+            return None
+        key = (str(device), B, T, img.dtype, plan, bool(with_scores))
+        cache = self.__dict__.setdefault("_graphs", {})
+        entry = cache.get(key)
+        if entry is False:
+            return None
+        if entry is not None and entry[4] != _lib.lib.iefvad_alloc_generation():
+            entry = None                        # a larger call re-allocated a workspace since the capture
+        n_wide = 7 * B * T * D
+        if entry is None:
+            try:
+                s_img, s_ev = torch.empty_like(img), torch.empty_like(ev)
+                s_out = torch.empty(n_wide + 2 * B * T, dtype=torch.float32, device=device)
+                wide = s_out[:n_wide].view(7, B, T, D)
+                logits = s_out[n_wide:n_wide + B * T].view(B, T, 1)
+                scores = s_out[n_wide + B * T:].view(B, T) if with_scores else None
+                s_img.copy_(img)
+                s_ev.copy_(ev)
+                side = torch.cuda.Stream(device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    launch(s_img, s_ev, wide, logits, scores)            # sizes the workspaces outside the capture
+                torch.cuda.current_stream(device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                l0 = _lib.lib.iefvad_launch_count()
+                with torch.cuda.graph(graph):
+                    launch(s_img, s_ev, wide, logits, scores)
+                n_kernels = _lib.lib.iefvad_launch_count() - l0
+                if len(cache) >= 4:                                      # a handful of shapes; drop the oldest
+                    cache.pop(next(iter(cache)))
+                entry = cache[key] = (graph, s_img, s_ev, s_out, _lib.lib.iefvad_alloc_generation(), n_kernels)
+            except Exception:
+                cache[key] = False
+                return None
+        graph, s_img, s_ev, s_out, _, n_kernels = entry
+        s_img.copy_(img)
+        s_ev.copy_(ev)
+        graph.replay()
+        _lib.lib.iefvad_add_launches(n_kernels)
+        out = s_out.clone()
+        return (out[:n_wide].view(7, B, T, D), out[n_wide:n_wide + B * T].view(B, T, 1),
+                out[n_wide + B * T:].view(B, T) if with_scores else None)
 
     def scores(self, img: torch.Tensor, ev: torch.Tensor, device=None, valid_lengths=None, rowmap=None
                ) -> Dict[str, torch.Tensor]:

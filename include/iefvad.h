@@ -277,6 +277,12 @@ int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stage
 
 /* number of CUDA kernels this library has launched since load (process-wide) */
 uint64_t iefvad_launch_count(void);
+/* bumped whenever a library workspace is (re)allocated: a CUDA graph captured around a forward call holds workspace
+ * addresses and must be re-captured once this value has changed (the Python module does that for its small-batch graphs) */
+uint64_t iefvad_alloc_generation(void);
+/* a caller that replays a CUDA graph captured around library calls reports the kernels of one replay here, so that
+ * iefvad_launch_count keeps counting launches rather than host calls */
+void iefvad_add_launches(uint64_t n);
 
 /* Per-kernel-class device timing of the model forward with CUDA events on the launching stream.
  * classes (IEFVAD_PROFILE_CLASSES = 12): 0 gemm_tc QKV in-projection, 1 attn_tc, 2 layernorm, 3 fuse, 4 classifier,

@@ -335,3 +335,29 @@ def test_valid_rows_mode_other_chunk_lengths(pkg, full, T):
         assert torch.equal(out["scores"], ref_s)
     else:
         assert ((out["scores"] - ref_s).abs() / ref_s).max().item() < 3e-4
+
+
+def test_small_forward_graph_replay_matches_eager(pkg, full, monkeypatch):
+    """Small problems replay the forward as one CUDA graph over static buffers: same bits as the eager launches, also
+    after a large call has re-allocated the library workspaces (the graph is re-captured) and after new weights."""
+    _, synth = pkg
+    m, _ = full["full_default"]
+    m.temporal.precision = "HH"
+    img, ev = synth.make_video(7, 256)
+    img, ev = img[None].cuda(), ev[None].cuda()
+    with torch.no_grad():
+        monkeypatch.setenv("IEFVAD_GRAPH_ROWS", "0")
+        eager = m(img, ev, None, None, None)
+        monkeypatch.setenv("IEFVAD_GRAPH_ROWS", "2048")
+        first = m(img, ev, None, None, None)                  # captures
+        again = m(img, ev, None, None, None)                  # replays
+        big_i, big_e = synth.make_video(8, 9000)
+        m(big_i[None].cuda(), big_e[None].cuda(), None, None, None)      # larger workspaces -> stale graph
+        after = m(img, ev, None, None, None)
+        for k in eager:
+            assert torch.equal(eager[k], first[k]) and torch.equal(eager[k], again[k]) and torch.equal(eager[k], after[k]), k
+        img2, ev2 = synth.make_video(9, 256)
+        out2 = m(img2[None].cuda(), ev2[None].cuda(), None, None, None)
+        monkeypatch.setenv("IEFVAD_GRAPH_ROWS", "0")
+        ref2 = m(img2[None].cuda(), ev2[None].cuda(), None, None, None)
+        assert torch.equal(out2["logits"], ref2["logits"]) and not torch.equal(out2["logits"], eager["logits"])
