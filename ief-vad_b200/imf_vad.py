@@ -231,7 +231,9 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         so host tensors must stay alive and unchanged until the stream has run.
         valid_lengths (host int64 [B]) + rowmap (device int32 [sum len], b * T + t of every valid row): the "valid rows"
         mode for zero-padded chunks - stages after the last attention core run on the valid rows only and the results
-        are COMPACT [sum len], bit-identical to the valid rows of the full forward."""
+        are COMPACT [sum len]: bit-identical to the valid rows of the full forward with `pad_dedup = False`, within
+        the rounding of one softmax term of them with the default pad de-duplication (rows past the valid length are
+        then taken to be the zero pads of `process_split` and are not read)."""
         if img.dim() != 3 or img.shape != ev.shape or img.shape[-1] != self.embed_dim:
             raise RuntimeError(f"expected two [B, T, {self.embed_dim}] tensors")
         codes = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
