@@ -31,6 +31,7 @@ int attn_tc(const AttnTcArgs& a, cudaStream_t stream);
 bool attn_long_supported(const AttnTcArgs& a);
 int attn_long(const AttnTcArgs& a, cudaStream_t stream);
 bool attn_short_supported(const AttnTcArgs& a);
+bool attn_short_enabled();      // IEFVAD_ATTN_SHORT != 0: the short kernel (and with it unpadded q / k rows) may be used
 int attn_short(const AttnTcArgs& a, cudaStream_t stream);
 
 // fp32 plan: qkv fp32 [B*T, 3*H*dh] (bias added, q unscaled) -> out fp32 [B*T, H*dh]

@@ -30,10 +30,16 @@ constexpr int kThreads = (kSoftmaxWarps + 2) * 32;
 template <int DH, int DHP>
 struct ShortCfg {
   static constexpr int TK = 256;                                   // keys covered by one S MMA
-  static constexpr uint32_t kQChunk = 128 * 128;                   // [128 rows x 64 columns] 128B-swizzled
-  static constexpr uint32_t kQTile = (DHP / 64) * kQChunk;
-  static constexpr uint32_t kKChunk = TK * 128;
-  static constexpr uint32_t kKBytes = (DHP / 64) * kKChunk;
+  // q / k rows of DHP elements are cut into column chunks of CW elements: 64 (128-byte swizzle) when DHP is a multiple
+  // of 64, else 32 (64-byte swizzle) - d_h = 96 then needs no padding to 128 (a quarter less q / k traffic)
+  static constexpr int CW = (DHP % 64 == 0) ? 64 : 32;
+  static constexpr int NCH = DHP / CW;
+  static constexpr uint32_t kRowB = CW * 2;                        // bytes per chunk row
+  static constexpr uint32_t kQChunk = 128 * kRowB;                 // [128 rows x CW columns], swizzled
+  static constexpr uint32_t kQTile = NCH * kQChunk;
+  static constexpr uint32_t kKChunk = TK * kRowB;
+  static constexpr uint32_t kKBytes = NCH * kKChunk;
+  static_assert(DHP % 32 == 0 && DHP >= DH, "q / k row length");
   static constexpr uint32_t kVSub = DH * 128;                      // [DH rows x 64 keys]
   static constexpr uint32_t kVBytes = (TK / 64) * kVSub;
   static constexpr uint32_t kOffK = 2 * kQTile;
@@ -127,17 +133,17 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_arrive_expect_tx(qk_full, uint32_t(nq(d)) * (Cfg::kQTile + Cfg::kKBytes / 2));
         for (int t = 0; t < nq(d); ++t)
 #pragma unroll
-          for (int c = 0; c < DHP / 64; ++c) {
-            tma_load_3d(&tmQ, qk_full, smem + t * Cfg::kQTile + c * Cfg::kQChunk, c * 64, d.row0 + t * 128, d.z);
-            tma_load_3d(&tmK, qk_full, smem + Cfg::kOffK + c * Cfg::kKChunk + t * Cfg::kQChunk, c * 64, d.row0 + t * 128, d.z);
+          for (int c = 0; c < Cfg::NCH; ++c) {
+            tma_load_3d(&tmQ, qk_full, smem + t * Cfg::kQTile + c * Cfg::kQChunk, c * Cfg::CW, d.row0 + t * 128, d.z);
+            tma_load_3d(&tmK, qk_full, smem + Cfg::kOffK + c * Cfg::kKChunk + t * Cfg::kQChunk, c * Cfg::CW, d.row0 + t * 128, d.z);
           }
       };
       auto prefetch = [&](const Item& nx) {
         for (int t = 0; t < nq(nx); ++t)
 #pragma unroll
-          for (int c = 0; c < DHP / 64; ++c) {
-            tma_prefetch_3d(&tmQ, c * 64, nx.row0 + t * 128, nx.z);
-            tma_prefetch_3d(&tmK, c * 64, nx.row0 + t * 128, nx.z);
+          for (int c = 0; c < Cfg::NCH; ++c) {
+            tma_prefetch_3d(&tmQ, c * Cfg::CW, nx.row0 + t * 128, nx.z);
+            tma_prefetch_3d(&tmK, c * Cfg::CW, nx.row0 + t * 128, nx.z);
           }
         for (int c = 0; c < nv(nx); ++c) tma_prefetch_3d(&tmVt, nx.row0 + c * 64, 0, nx.z);
       };
@@ -176,10 +182,13 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       auto issue_s = [&](int t) {
         const uint32_t d = tmem_base + uint32_t(t * 256);
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {   // only the DH real columns of the DHP-padded rows
-          const int c = kk >> 2, k4 = kk & 3;
-          umma_bf16(d, make_smem_desc_sw128(sq + t * Cfg::kQTile + c * Cfg::kQChunk) + uint64_t(2 * k4),
-                    make_smem_desc_sw128(sk + c * Cfg::kKChunk) + uint64_t(2 * k4), idesc_s, kk != 0 ? 1u : 0u);
+        for (int kk = 0; kk < DH / 16; ++kk) {   // only the DH real columns of DHP-padded rows
+          constexpr int KPC = Cfg::CW / 16;      // 16-element K steps per column chunk
+          const int c = kk / KPC, ks = kk % KPC;
+          const uint32_t qa = sq + t * Cfg::kQTile + c * Cfg::kQChunk, ka = sk + c * Cfg::kKChunk;
+          const uint64_t dq = Cfg::CW == 64 ? make_smem_desc_sw128(qa) : make_smem_desc_sw64(qa);
+          const uint64_t dk = Cfg::CW == 64 ? make_smem_desc_sw128(ka) : make_smem_desc_sw64(ka);
+          umma_bf16(d, dq + uint64_t(2 * ks), dk + uint64_t(2 * ks), idesc_s, kk != 0 ? 1u : 0u);
         }
         tc_commit(&s_full[t]);
       };
@@ -392,8 +401,9 @@ int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
   // dense: [B*H, T, dhp]; ragged items: [H, T = all packed rows, dhp] with `n_chunks` row ranges (AttnTcArgs.items)
   const uint64_t BH = a.items ? uint64_t(a.H) : uint64_t(a.B) * a.H;
   CUtensorMap tq, tk, tv;
-  IEF_TRY(make_tmap_3d(&tq, a.q, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, 128, 1));
-  IEF_TRY(make_tmap_3d(&tk, a.k, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, 64, 128, 1));
+  const int qk_sw = Cfg::CW == 64 ? TM_SWIZZLE_128B : TM_SWIZZLE_64B;
+  IEF_TRY(make_tmap_3d(&tq, a.q, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, Cfg::CW, 128, 1, qk_sw));
+  IEF_TRY(make_tmap_3d(&tk, a.k, DHP, a.T, BH, uint64_t(DHP) * 2, uint64_t(a.T) * DHP * 2, Cfg::CW, 128, 1, qk_sw));
   IEF_TRY(make_tmap_3d(&tv, a.vt, a.T, DH, BH, uint64_t(a.Tpad) * 2, uint64_t(DH) * a.Tpad * 2, 64, DH, 1));
   const int n_items = a.items ? a.n_chunks * a.H : int(BH);
   const int grid = n_items < num_sms ? n_items : num_sms;
@@ -425,8 +435,13 @@ int launch_attn_short(const AttnTcArgs& a, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
-bool attn_short_supported(const AttnTcArgs& a) {
+bool attn_short_enabled() {
   static const int env_off = [] { const char* e = getenv("IEFVAD_ATTN_SHORT"); return (e && atoi(e) == 0) ? 1 : 0; }();
+  return !env_off;
+}
+
+bool attn_short_supported(const AttnTcArgs& a) {
+  const int env_off = attn_short_enabled() ? 0 : 1;
   if (a.items) return !a.attn_mask && !a.key_pad;      // ragged items exist only here (every item <= 256 rows)
   return !env_off && a.T <= 256 && !a.attn_mask && !a.key_pad && uint64_t(a.B) * a.H < (1ull << 31);
 }
@@ -440,10 +455,12 @@ int attn_short(const AttnTcArgs& a, cudaStream_t stream) {
   }
 #define IEF_ATTN_SHORT(DH_, DHP_) \
   if (a.dh == DH_ && a.dhp == DHP_) return launch_attn_short<DH_, DHP_>(a, num_sms, stream);
+  IEF_ATTN_SHORT(96, 96)      // unpadded q / k rows (32-column chunks, 64-byte swizzle)
   IEF_ATTN_SHORT(96, 128)
   IEF_ATTN_SHORT(64, 64)
   IEF_ATTN_SHORT(128, 128)
   IEF_ATTN_SHORT(32, 64)
+  IEF_ATTN_SHORT(32, 32)
 #undef IEF_ATTN_SHORT
   set_error("attn_short: unsupported head dim %d (padded %d); supported: 32, 64, 96, 128", a.dh, a.dhp);
   return IEFVAD_ERR_INVALID;

@@ -251,6 +251,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// K-major tile stored as rows of 64 bytes (32 16-bit elements) with the 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B):
+// 8-row groups are 512 B apart, layout_type = 4 (cute::UMMA::LayoutType::SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
 // Same, with the B operand MN-major (N contiguous in smem): used for P.V where V is stored [keys, d] row-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int M, int N) {
   return make_idesc_bf16(M, N) | (1u << 16);

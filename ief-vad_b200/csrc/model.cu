@@ -352,6 +352,10 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       if (dedup) IEF_TRY(inverse_rowmap_items(items_dev.as<ChunkItem>(), aux_dev.as<ChunkAux>(), n_items, inv_map.as<int>(), stream));
       else IEF_TRY(inverse_rowmap(vr->rowmap + out0, vr->row_base + row0, Mo, M, inv_map.as<int>(), num_sms, stream));
     }
+    // q / k rows: d_h padded to a multiple of 64 for the 128-byte-swizzled kernels; the short-sequence kernel takes
+    // 32-column chunks (64-byte swizzle), so d_h = 96 goes unpadded there (a quarter less q / k traffic)
+    static const bool qk_pad = [] { const char* e = getenv("IEFVAD_QK_PAD"); return e && atoi(e) != 0; }();   // A/B knob
+    const int dhq = (!fp32_plan && T <= 256 && dh % 32 == 0 && attn_short_enabled() && !qk_pad) ? dh : dhp;
     for (int m = 0; m < 2; ++m) {
       const bool ragged = vr && vr->chunk_start && vr->chunk_valid;
       const uint8_t* in = static_cast<const uint8_t*>(inputs[m]) + (ragged ? 0 : size_t(row0) * D * in_esize);
@@ -397,14 +401,14 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           EpiParams e1;
           e1.hi_fp16 = a16;
           e1.mode = EPI_QKV; e1.bias = ip.b; e1.q = qb.as<bf16>(); e1.k = kb.as<bf16>(); e1.vt = vtb.as<bf16>();
-          e1.T = dedup ? int(Me) : int(T); e1.H = H; e1.dh = dh; e1.dhp = dhp; e1.Tpad = dedup ? int(Me) : Tpad; e1.D = D; e1.qscale = qscale;
+          e1.T = dedup ? int(Me) : int(T); e1.H = H; e1.dh = dh; e1.dhp = dhq; e1.Tpad = dedup ? int(Me) : Tpad; e1.D = D; e1.qscale = qscale;
           GemmTcArgs g1;
           g1.A_hi = (i == 0) ? x16 : a_hi.as<bf16>(); g1.A_lo = a_lo.as<bf16>(); g1.W_hi = a16 ? ip.w_h16 : ip.w_hi; g1.W_lo = ip.w_lo;
           g1.M = int(Me); g1.N = 3 * D; g1.K = D; g1.lda = D; g1.ldw = D; g1.nsplit = sp ? 3 : 1; g1.fp16 = a16;
           IEF_PROF(KC_GEMM_QKV, 6.0 * Me * D * D, gemm_tc(g1, e1, num_sms, stream));
           AttnTcArgs at;
           at.q = qb.as<bf16>(); at.k = kb.as<bf16>(); at.vt = vtb.as<bf16>(); at.out = h_hi.as<bf16>(); at.ldo = D;
-          at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhp; at.Tpad = Tpad;
+          at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhq; at.Tpad = Tpad;
           if (dedup) { at.B = 1; at.T = int(Me); at.Tpad = int(Me); at.items = items_dev.as<int>(); at.n_chunks = n_items; }
           at.fp16 = a16; at.out_fp16 = a16;
           if (direct_compact && last) at.row_out = inv_map.as<int>();

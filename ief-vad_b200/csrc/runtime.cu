@@ -139,11 +139,11 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ou
 }
 
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, int swizzle) {
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, box2};
-  return encode(out, base, 3, dims, strides, box, TM_BF16, TM_SWIZZLE_128B);
+  return encode(out, base, 3, dims, strides, box, TM_BF16, swizzle);
 }
 
 int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
