@@ -252,6 +252,25 @@ class Evaluator:
         res["scores"] = scores
         return res
 
+    def step_breakdown(self, reps: int = 5, host_inputs: bool = False) -> Dict[str, float]:
+        """Where a step's device time goes: forward over my chunks | the single collective (+ re-ordering into list
+        order) | ranking (AUC / AP of every subset).  CUDA events on the launching stream, mean of `reps` steps.  At
+        world > 1 the collective's time includes waiting for the slowest rank's forward."""
+        marks = []
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            packed = self.local_scores(host_inputs)
+            ev[1].record()
+            scores = self.gather(packed)
+            ev[2].record()
+            self.metrics_async(scores)
+            ev[3].record()
+            marks.append(ev)
+        torch.cuda.current_stream(self.device).synchronize()
+        names = ("forward_ms", "collective_ms", "ranking_ms")
+        return {nm: round(sum(ev[i].elapsed_time(ev[i + 1]) for ev in marks) / reps, 4) for i, nm in enumerate(names)}
+
     # bytes moved by a host-input step (for bench.py's e2e block)
     def h2d_bytes(self) -> int:
         if self._ragged is not None:

@@ -214,6 +214,128 @@ def eval_loop_case():
          AP=np.float64(ap), ret=np.array([float(x) for x in ret]) if ret is not None else np.zeros(0))
 
 
+class _Recorder(torch.nn.Module):
+    """Wraps the unmodified reference model and records, per call, what the reference's eval loop derives from the
+    forward besides the scores (train/ucf_test.py:124-144): w_i.mean(-1), w_e.mean(-1) and sample rows of fused /
+    image_mu / event_mu (the full [len, 768] tensors would be 240 MB per tensor on config 2)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        self.wi, self.we, self.rows = [], [], []
+        self.len_cur = 0             # set by the loader: the loop's own `lengths` over-counts when T % 256 == 0
+
+    def forward(self, img, ev, padding_mask, text, lengths):
+        out = self.model(img, ev, padding_mask, text, lengths)
+        n = self.len_cur
+        flat = lambda t: t.reshape(t.shape[0] * t.shape[1], t.shape[2])  # noqa: E731
+        self.wi.append(flat(out["w_i"]).mean(dim=-1).numpy()[:n].copy())
+        self.we.append(flat(out["w_e"]).mean(dim=-1).numpy()[:n].copy())
+        self.rows.append(np.stack([flat(out[k]).numpy()[0].copy() for k in ("fused", "image_mu", "event_mu")]))
+        return out
+
+
+def config2_case():
+    """BASELINE configs[1] AT FULL SIZE (the bench workload): the reference's own train/ucf_test.py:test() over all 290
+    synthetic UCF-shaped videos (77 788 frames, T up to 4096 = 17 chunks), default-seed full-size model, CPU fp32."""
+    T = synth.config_lengths("ucf")
+    n = len(T)
+    classes = synth.config_classes("ucf", n)
+    gt = synth.make_gt(T, classes)
+    model = _Recorder(synth.build_model(RefMMFMIL, seed=0).eval())
+    digest = synth.state_digest(model.model.state_dict())
+    from data.tools import process_split
+
+    class Loader:
+        def __iter__(self):
+            for v in range(n):
+                img, ev = synth.make_video(v, int(T[v]))
+                fi, ln = process_split(img.numpy(), 256)
+                fe, _ = process_split(ev.numpy(), 256)
+                model.len_cur = int(ln)
+                yield (torch.from_numpy(fi)[None], torch.from_numpy(fe)[None], [classes[v]], torch.tensor([ln]))
+
+    args = types.SimpleNamespace(exp_name="golden", dataset="ucfcrime")
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    captured = {}
+    real_auc = ref_ucf_test.roc_auc_score
+
+    def spy(gt_, pred):
+        captured.setdefault("first", np.asarray(pred)[::16].copy())
+        return real_auc(gt_, pred)
+
+    try:
+        ref_ucf_test.roc_auc_score = spy
+        ret = ref_ucf_test.test(args, model, Loader(), 256, None, gt, "cpu")
+    finally:
+        ref_ucf_test.roc_auc_score = real_auc
+        os.chdir(cwd)
+    scores = captured["first"]
+    assert scores.size == int(T.sum())
+    rep = np.repeat(scores, 16)
+    auc, ap = roc_auc_score(gt, rep), average_precision_score(gt, rep)
+    # class-wise AUC / AP (:164-178) and Ano-AUC (:336-353) recomputed with sklearn on the captured scores
+    off = np.concatenate([[0], np.cumsum(T)])
+    keys = list(dict.fromkeys(classes))
+    cw = np.full((len(keys), 2), np.nan)
+    for c, key in enumerate(keys):
+        idx = np.concatenate([np.arange(off[v], off[v + 1]) for v in range(n) if classes[v] == key])
+        g = gt.reshape(-1, 16)[idx].reshape(-1)
+        if g.sum() == 0:
+            continue
+        r = np.repeat(scores[idx], 16)
+        cw[c] = roc_auc_score(g, r), average_precision_score(g, r)
+    idx = np.concatenate([np.arange(off[v], off[v + 1]) for v in range(n) if classes[v] != "Normal"])
+    ano = roc_auc_score(gt.reshape(-1, 16)[idx].reshape(-1), np.repeat(scores[idx], 16))
+    print("config 2: reference test() returned", ret, "recomputed", auc, ap, "ano", ano)
+    save("config2_ucf.npz", digest=np.array(digest), lengths=T, classes=np.array(classes),
+         scores=scores.astype(np.float32), AUC=np.float64(auc), AP=np.float64(ap), ano_AUC=np.float64(ano),
+         class_keys=np.array(keys), classwise=cw, wi_mean=np.concatenate(model.wi).astype(np.float32),
+         we_mean=np.concatenate(model.we).astype(np.float32), first_rows=np.stack(model.rows).astype(np.float32),
+         ret=np.array([float(x) for x in ret]) if ret is not None else np.zeros(0))
+
+
+def config3_case():
+    """BASELINE configs[2] AT FULL SIZE: 800 synthetic XD-Violence-shaped videos (684 801 frames) through the
+    per-video loop of train/xd_test.py:70-119 (the same loop as ucf_test: process_split chunks -> model ->
+    sigmoid(logits[:len])); scores + overall AUC / AP with sklearn."""
+    T = synth.config_lengths("xd")
+    n = len(T)
+    classes = synth.config_classes("xd", n)
+    gt = synth.make_gt(T, classes)
+    model = synth.build_model(RefMMFMIL, seed=0).eval()
+    from data.tools import process_split
+    out_scores = []
+    for v in range(n):
+        img, ev = synth.make_video(v, int(T[v]))
+        fi, ln = process_split(img.numpy(), 256)
+        fe, _ = process_split(ev.numpy(), 256)
+        fi, fe = torch.from_numpy(fi), torch.from_numpy(fe)
+        if ln < 256:
+            fi, fe = fi[None], fe[None]
+        out = model(fi, fe, None, None, None)
+        lg = out["logits"].reshape(-1, 1)
+        out_scores.append(torch.sigmoid(lg[0:ln].squeeze(-1)).numpy())
+    scores = np.concatenate(out_scores)
+    rep = np.repeat(scores.astype(np.float64), 16)
+    auc, ap = roc_auc_score(gt, rep), average_precision_score(gt, rep)
+    print("config 3:", scores.size, "frames, AUC", auc, "AP", ap)
+    save("config3_xd.npz", digest=np.array(synth.state_digest(model.state_dict())), lengths=T,
+         classes=np.array(classes), scores=scores.astype(np.float32), AUC=np.float64(auc), AP=np.float64(ap))
+
+
+def config4_b128_case():
+    """Config 4 at the batch train/ucf_train.py:44-48 really builds (two 64-clip loaders concatenated -> B = 128):
+    eval-mode forward + the reference's CLAS2, inputs from synth.make_c4_batch(128)."""
+    model = synth.build_model(RefMMFMIL, seed=0).eval()
+    img, ev, lengths, labels = synth.make_c4_batch(128)
+    out = model(img, ev, None, None, lengths)
+    loss = ref_CLAS2(out["logits"], labels, lengths, "cpu")
+    save("config4_b128.npz", digest=np.array(synth.state_digest(model.state_dict())), lengths=lengths.numpy(),
+         labels=labels.numpy(), logits=out["logits"].numpy().reshape(128, 256), loss=np.float64(float(loss)))
+
+
 def sklearn_cases():
     rng = np.random.default_rng(12)
     arrays = {}
@@ -358,3 +480,9 @@ if __name__ == "__main__":
             tools_cases()
         if "event" in which:
             event_cases()
+        if "config2" in which:            # full-size cases: not in the default list (about 20 s / 3 min of CPU)
+            config2_case()
+        if "config3" in which:
+            config3_case()
+        if "config4" in which:
+            config4_b128_case()
