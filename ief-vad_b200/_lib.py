@@ -32,12 +32,15 @@ _SIGS = {
     "iefvad_model_set_param": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
     "iefvad_model_set_plan": (_i, [_vp, _i]),
     "iefvad_model_get_plan": (_i, [_vp]),
+    "iefvad_model_set_option": (_i, [_vp, C.c_char_p, _i64]),
+    "iefvad_model_check_finite": (_i, [_vp, C.POINTER(C.c_int), _vp]),
     "iefvad_model_set_max_rows": (_i, [_vp, _i64]),
     "iefvad_model_forward": (_i, [_vp, _vp, _vp, _i, _i64, _i64] + [_vp] * 9 + [_vp]),
     "iefvad_model_forward_host": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
     "iefvad_model_forward_host_to_device": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
     "iefvad_model_set_host_part_rows": (_i, [_vp, _i64]),
     "iefvad_model_set_pad_dedup": (_i, [_vp, _i]),
+    "iefvad_model_set_eval_outputs": (_i, [_vp] * 6),
     "iefvad_event_image": (_i, [_vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
     "iefvad_model_forward_scores_ragged": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "iefvad_model_forward_scores": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -43,7 +43,7 @@ def _fingerprint() -> str:
             if f.endswith((".cu", ".cuh", ".h")):
                 with open(os.path.join(root, f), "rb") as fh:
                     h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS).encode() + b"|cudart shared")
     return h.hexdigest()
 
 
@@ -69,7 +69,9 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    # the CUDA runtime is linked dynamically (libcudart.so.12: the copy torch has already loaded, else the toolkit's)
+    cmd = [nvcc, "-shared", "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB_PATH, *objs,
+           "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

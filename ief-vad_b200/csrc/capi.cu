@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "attention.cuh"
@@ -28,6 +29,10 @@ struct iefvad_model {
   DevBuf host_in[2][2], host_out[5], host_logits, host_scores;   // host_out: fused, mu x2, logvar x2 (scratch)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_start = nullptr;
+  // optional extra outputs of the evaluation forward (iefvad_model_set_eval_outputs): compact DEVICE buffers of the caller
+  float* ex_wi_mean = nullptr;
+  float* ex_we_mean = nullptr;
+  float* ex_wide[3] = {nullptr, nullptr, nullptr};      // fused, image_mu, event_mu
   int64_t host_part_rows = 32768;
   uint64_t host_seq = 0;          // parts issued so far: the ping-pong of the input buffers continues across calls
 };
@@ -107,6 +112,30 @@ int iefvad_model_set_plan(iefvad_model* m, int plan) {
 }
 
 int iefvad_model_get_plan(const iefvad_model* m) { return m ? m->impl.plan : 0; }
+
+int iefvad_model_set_option(iefvad_model* m, const char* name, int64_t value) {
+  IEF_CHECK(m && name, "iefvad_model_set_option: null argument");
+  const std::string key(name);
+  if (key == "refine_fused") {
+    IEF_CHECK(value >= -1 && value <= 1, "refine_fused: -1 (auto), 0 (off), 1 (on)");
+    m->impl.refine_fused = int(value);
+  } else {
+    set_error("iefvad_model_set_option: unknown option '%s'", name);
+    return IEFVAD_ERR_INVALID;
+  }
+  return IEFVAD_OK;
+}
+
+int iefvad_model_check_finite(iefvad_model* m, int* nonfinite_host, void* stream) {
+  IEF_CHECK(m && nonfinite_host, "iefvad_model_check_finite: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int flags[4] = {0, 0, 0, 0};
+  IEF_CUDA(cudaMemcpyAsync(flags, m->impl.status.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  IEF_CUDA(cudaMemsetAsync(m->impl.status.p, 0, sizeof(flags), st));
+  IEF_CUDA(cudaStreamSynchronize(st));
+  *nonfinite_host = flags[0];
+  return IEFVAD_OK;
+}
 
 int iefvad_model_set_max_rows(iefvad_model* m, int64_t max_rows) {
   IEF_CHECK(m && max_rows >= 1, "iefvad_model_set_max_rows: need a model and max_rows >= 1");
@@ -239,8 +268,14 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
     IEF_CUDA(cudaStreamWaitEvent(st, m->ev_copied[buf], 0));
     float* o[5];
     for (int i = 0; i < 5; ++i) o[i] = m->host_out[i].as<float>();
-    IEF_TRY(m->impl.forward(m->host_in[buf][0].p, m->host_in[buf][1].p, in_dtype, Bs, T, o[0], ldev + o0, o[1], o[2], o[3],
-                            o[4], nullptr, nullptr, sdev ? sdev + o0 : nullptr, st, valid_len_host ? &vr : nullptr));
+    for (int i = 0; i < 3; ++i)
+      if (m->ex_wide[i]) o[i] = m->ex_wide[i] + o0 * D;               // the caller wants this tensor: write it there
+    m->impl.eval_wi_mean = m->ex_wi_mean ? m->ex_wi_mean + o0 : nullptr;
+    m->impl.eval_we_mean = m->ex_we_mean ? m->ex_we_mean + o0 : nullptr;
+    const int frc = m->impl.forward(m->host_in[buf][0].p, m->host_in[buf][1].p, in_dtype, Bs, T, o[0], ldev + o0, o[1], o[2], o[3],
+                                    o[4], nullptr, nullptr, sdev ? sdev + o0 : nullptr, st, valid_len_host ? &vr : nullptr);
+    m->impl.eval_wi_mean = m->impl.eval_we_mean = nullptr;
+    IEF_TRY(frc);
     j0 += nvalid;
     IEF_CUDA(cudaEventRecord(m->ev_consumed[buf], st));
     if (logits_host) IEF_CUDA(cudaMemcpyAsync(logits_host + r0, ldev + r0, nr * 4, cudaMemcpyDeviceToHost, st));
@@ -297,8 +332,26 @@ int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev
   for (auto& b : m->host_out) IEF_TRY(b.reserve((rows ? rows : 1) * m->impl.D * 4));
   float* o[5];
   for (int i = 0; i < 5; ++i) o[i] = m->host_out[i].as<float>();
-  return m->impl.forward(img, ev, in_dtype, B, T, o[0], logits, o[1], o[2], o[3], o[4], nullptr, nullptr, scores, st,
-                         valid_len_host ? &vr : nullptr);
+  for (int i = 0; i < 3; ++i)
+    if (m->ex_wide[i]) o[i] = m->ex_wide[i];
+  m->impl.eval_wi_mean = m->ex_wi_mean;
+  m->impl.eval_we_mean = m->ex_we_mean;
+  const int rc = m->impl.forward(img, ev, in_dtype, B, T, o[0], logits, o[1], o[2], o[3], o[4], nullptr, nullptr, scores, st,
+                                 valid_len_host ? &vr : nullptr);
+  m->impl.eval_wi_mean = m->impl.eval_we_mean = nullptr;
+  return rc;
+}
+
+int iefvad_model_set_eval_outputs(iefvad_model* m, float* wi_mean, float* we_mean, float* fused, float* image_mu,
+                                  float* event_mu) {
+  IEF_CHECK(m, "null model");
+  IEF_CHECK((wi_mean == nullptr) == (we_mean == nullptr), "iefvad_model_set_eval_outputs: wi_mean and we_mean go together");
+  m->ex_wi_mean = wi_mean;
+  m->ex_we_mean = we_mean;
+  m->ex_wide[0] = fused;
+  m->ex_wide[1] = image_mu;
+  m->ex_wide[2] = event_mu;
+  return IEFVAD_OK;
 }
 
 int iefvad_model_set_pad_dedup(iefvad_model* m, int on) {

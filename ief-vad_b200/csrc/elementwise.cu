@@ -231,6 +231,65 @@ fuse_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, co
   }
 }
 
+// The same fusion with one warp per row, which also reduces w_i / w_e over the row: the evaluation loop of the reference
+// keeps only w_i.mean(-1) and w_e.mean(-1) per frame (train/ucf_test.py:124-131) - 8 bytes per row instead of 6 KB.
+__global__ void __launch_bounds__(kThreads)
+fuse_rows_kernel(const float4* __restrict__ mu_i, const float4* __restrict__ mu_e, const float4* __restrict__ lv_i,
+                 const float4* __restrict__ lv_e, long long rows, int D4, float factor, float eps, float inv_d,
+                 float* __restrict__ wi_mean, float* __restrict__ we_mean, float4* __restrict__ fused,
+                 bf16* __restrict__ fused_hi, bf16* __restrict__ fused_lo, int hi_fp16) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    float si = 0.f, se = 0.f;
+    for (int c = lane; c < D4; c += 32) {
+      const long long i = row * D4 + c;
+      const float4 a = __ldcs(mu_i + i), b = __ldcs(mu_e + i), cc = __ldcs(lv_i + i), d = __ldcs(lv_e + i);
+      const float mi[4] = {a.x, a.y, a.z, a.w}, me[4] = {b.x, b.y, b.z, b.w};
+      const float li[4] = {cc.x, cc.y, cc.z, cc.w}, le[4] = {d.x, d.y, d.z, d.w};
+      float f[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float ri = __fmul_rn(factor, expf(-li[e]));
+        const float re = __fmul_rn(factor, expf(-le[e]));
+        const float den = __fadd_rn(__fadd_rn(ri, re), eps);
+        const float wi = __fdiv_rn(ri, den), we = __fdiv_rn(re, den);
+        si += wi;
+        se += we;
+        f[e] = __fadd_rn(__fmul_rn(wi, mi[e]), __fmul_rn(we, me[e]));
+      }
+      if (fused) fused[i] = make_float4(f[0], f[1], f[2], f[3]);
+      if (fused_hi && hi_fp16) {
+        const __half2 h01 = __floats2half2_rn(f[0], f[1]), h23 = __floats2half2_rn(f[2], f[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h01);
+        u.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(fused_hi + i * 4) = u;
+        if (fused_lo) {
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(f[0] - f01.x, f[1] - f01.y), l23 = __floats2half2_rn(f[2] - f23.x, f[3] - f23.y);
+          uint2 ul;
+          ul.x = *reinterpret_cast<const uint32_t*>(&l01);
+          ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(fused_lo + i * 4) = ul;
+        }
+      } else if (fused_hi) {
+        bf16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_bf16(f[e], h[e], l[e]);
+        *reinterpret_cast<uint2*>(fused_hi + i * 4) = *reinterpret_cast<uint2*>(h);
+        if (fused_lo) *reinterpret_cast<uint2*>(fused_lo + i * 4) = *reinterpret_cast<uint2*>(l);
+      }
+    }
+    si = warp_sum(si);
+    se = warp_sum(se);
+    if (lane == 0) {
+      wi_mean[row] = si * inv_d;
+      we_mean[row] = se * inv_d;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 inverse_rowmap_kernel(const int* __restrict__ rowmap, long long row_base, long long n_rows, int* __restrict__ inv) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += (long long)gridDim.x * blockDim.x)
@@ -284,7 +343,8 @@ to_half_kernel(const float* __restrict__ in, long long n, __half* __restrict__ o
 // ---------------------------------------------------------------- classifier: warp-per-row fp32 dot product
 __global__ void __launch_bounds__(kThreads)
 classifier_kernel(const float* __restrict__ x, long long M, int D, const float* __restrict__ w,
-                  const float* __restrict__ bias, float* __restrict__ logits, float* __restrict__ scores) {
+                  const float* __restrict__ bias, float* __restrict__ logits, float* __restrict__ scores,
+                  int* __restrict__ nonfinite) {
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float b = __ldg(bias);
@@ -303,6 +363,9 @@ classifier_kernel(const float* __restrict__ x, long long M, int D, const float* 
     if (lane == 0) {
       logits[row] = s;
       if (scores) scores[row] = 1.f / (1.f + expf(-s));
+      // range guard of the 16-bit plans: an operand that overflowed fp16 / bf16 anywhere upstream reaches the last
+      // activation row as inf / NaN (every stage propagates them), so one test per row here sees all of them
+      if (nonfinite && !(fabsf(s) <= 3.0e38f)) atomicOr(nonfinite, 1);
     }
   }
 }
@@ -399,6 +462,20 @@ int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* l
   return IEFVAD_OK;
 }
 
+int fuse_rows(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long rows, int D, float factor,
+              float eps, float* wi_mean, float* we_mean, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
+              cudaStream_t stream, int hi_fp16) {
+  IEF_CHECK(D % 4 == 0 && wi_mean && we_mean, "fuse_rows: D %% 4 == 0 and both mean outputs are required");
+  if (rows == 0) return IEFVAD_OK;
+  fuse_rows_kernel<<<grid_for(rows * 32, num_sms), kThreads, 0, stream>>>(
+      reinterpret_cast<const float4*>(mu_i), reinterpret_cast<const float4*>(mu_e), reinterpret_cast<const float4*>(lv_i),
+      reinterpret_cast<const float4*>(lv_e), rows, D / 4, factor, eps, 1.0f / float(D), wi_mean, we_mean,
+      reinterpret_cast<float4*>(fused), fused_hi, fused_lo, hi_fp16);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
 int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long row_base, long long n_rows, int D,
                 bf16* ctx_c, float* x_c, int num_sms, cudaStream_t stream) {
   IEF_CHECK(D % 8 == 0, "gather_rows: D=%d must be a multiple of 8", D);
@@ -448,10 +525,10 @@ int to_half(const float* in, long long n, void* out_f16, int num_sms, cudaStream
 }
 
 int classifier(const float* x, long long M, int D, const float* w, const float* bias, float* logits, float* scores,
-               int num_sms, cudaStream_t stream) {
+               int num_sms, cudaStream_t stream, int* nonfinite) {
   IEF_CHECK(D % 4 == 0, "classifier: D=%d must be a multiple of 4", D);
   if (M == 0) return IEFVAD_OK;
-  classifier_kernel<<<grid_for(M * 32, num_sms), kThreads, 0, stream>>>(x, M, D, w, bias, logits, scores);
+  classifier_kernel<<<grid_for(M * 32, num_sms), kThreads, 0, stream>>>(x, M, D, w, bias, logits, scores, nonfinite);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

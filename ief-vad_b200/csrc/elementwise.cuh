@@ -41,6 +41,12 @@ int fuse(const float* mu_i, const float* mu_e, const float* lv_i, const float* l
          float eps, float* w_i, float* w_e, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
          cudaStream_t stream, int hi_fp16 = 0 /* fused_hi receives fp16 instead of bf16 */);
 
+// The same with one warp per row, which also writes the row means of w_i / w_e (what the reference's evaluation loop keeps
+// of them, train/ucf_test.py:124-131) instead of the [rows, D] weight tensors.
+int fuse_rows(const float* mu_i, const float* mu_e, const float* lv_i, const float* lv_e, long long rows, int D, float factor,
+              float eps, float* wi_mean, float* we_mean, float* fused, bf16* fused_hi, bf16* fused_lo, int num_sms,
+              cudaStream_t stream, int hi_fp16 = 0);
+
 // compact the rows listed in rowmap (minus row_base): ctx_c[j] = ctx[rowmap[j] - base] (16-bit rows), x_c[j] = x[...] (fp32)
 int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long row_base, long long n_rows, int D,
                 bf16* ctx_c, float* x_c, int num_sms, cudaStream_t stream);
@@ -49,7 +55,8 @@ int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long ro
 int to_half(const float* in, long long n, void* out_f16, int num_sms, cudaStream_t stream);
 
 // logits[row] = x[row, :] . w + bias;  scores (optional) = sigmoid(logits)
+// nonfinite (optional device int): bit 0 is set when a logit is inf / NaN (the range guard of the 16-bit plans)
 int classifier(const float* x, long long M, int D, const float* w, const float* bias, float* logits, float* scores,
-               int num_sms, cudaStream_t stream);
+               int num_sms, cudaStream_t stream, int* nonfinite = nullptr);
 
 }  // namespace iefvad

@@ -2,6 +2,7 @@
 #include "model.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -9,8 +10,8 @@
 
 namespace iefvad {
 
-static unsigned long long g_alloc_generation = 0;
-unsigned long long alloc_generation() { return g_alloc_generation; }
+static std::atomic<unsigned long long> g_alloc_generation{0};
+unsigned long long alloc_generation() { return g_alloc_generation.load(); }
 
 int DevBuf::reserve(size_t need) {
   if (need <= bytes) return IEFVAD_OK;
@@ -164,6 +165,8 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
   IEF_TRY(params_hi.reserve(bf_elems * sizeof(bf16)));
   IEF_TRY(params_lo.reserve(bf_elems * sizeof(bf16)));
   IEF_CUDA(cudaMemset(params_f32.p, 0, params_f32.bytes));
+  IEF_TRY(status.reserve(4 * sizeof(int)));
+  IEF_CUDA(cudaMemset(status.p, 0, status.bytes));
   size_t fo = 0, bo = 0, ho = 0;
   for (auto& w : wants) {
     *w.dst = params_f32.as<float>() + fo;
@@ -205,6 +208,11 @@ int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, floa
     slots.erase(std::string("@heads_w.") + mods[m]);
     slots.erase(std::string("@heads_b.") + mods[m]);
   }
+  refine_contig = R > 0;
+  for (int i = 0; i < R; ++i) {
+    if (ref2[i].w_h16 != ref1[i].w_h16 + (long long)D * D) refine_contig = false;
+    if (i + 1 < R && ref1[i + 1].w_h16 != ref2[i].w_h16 + (long long)D * D) refine_contig = false;
+  }
   return IEFVAD_OK;
 }
 
@@ -236,7 +244,7 @@ int Model::reserve_workspace(long long rows, int B, int T, bool fp32_plan) {
   if (!fp32_plan) {
     IEF_TRY(a_hi.reserve(act * 2));
     IEF_TRY(a_lo.reserve(act * 2));
-    IEF_TRY(h_hi.reserve(act * 2));
+    IEF_TRY(h_hi.reserve(act * 2 + size_t(256) * D * 2));      // + one 256-row tile: the fused refinement chain's scratch
     IEF_TRY(h_lo.reserve(act * 2));
     const int Tpad = (T + 7) / 8 * 8;
     IEF_TRY(qb.reserve(size_t(B) * H * T * dhp * 2));
@@ -346,6 +354,11 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       }
     }
     const int n_items = dedup ? int(items_host.size()) : 0;
+    double attn_flops = 4.0 * double(Me) * double(T) * D;      // executed: QK^T + PV over the keys each query really sees
+    if (dedup) {
+      attn_flops = 0.0;
+      for (const ChunkItem& it : items_host) attn_flops += 4.0 * double(it.rows) * double(it.rows) * D;
+    }
     if (dedup && n_items == 0) continue;                 // no valid row in this slab
     if (direct_compact) {
       IEF_TRY(inv_map.reserve(size_t(Me) * sizeof(int)));
@@ -412,7 +425,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           if (dedup) { at.B = 1; at.T = int(Me); at.Tpad = int(Me); at.items = items_dev.as<int>(); at.n_chunks = n_items; }
           at.fp16 = a16; at.out_fp16 = a16;
           if (direct_compact && last) at.row_out = inv_map.as<int>();
-          IEF_PROF(KC_ATTN_TC, 4.0 * Me * T * D, attn_tc(at, stream));
+          IEF_PROF(KC_ATTN_TC, attn_flops, attn_tc(at, stream));
           // after the last attention core only the valid rows go on: gather (context, residual) into compact matrices
           const bool compact = vr && last;
           const long long Mc = compact ? Mo : Me;
@@ -478,11 +491,30 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     // refinement step moves 7.5 KB per row through HBM instead of 12 KB (no separate fp32 copy of x)
     const bool pair16 = r16 && R > 0;
     float* xcur = (R == 0) ? fused_out : (pair16 ? nullptr : x32.as<float>());
-    IEF_PROF(KC_FUSE, double(Mo) * D * 28, fuse(image_mu + out0 * D, event_mu + out0 * D, image_logvar + out0 * D, event_logvar + out0 * D, Mo * D,
-                 factor, eps, w_i ? w_i + out0 * D : nullptr, w_e ? w_e + out0 * D : nullptr, xcur, (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>(),
-                 ((rsp || pair16) && R > 0) ? a_lo.as<bf16>() : nullptr, num_sms, stream, r16 ? 1 : 0));
+    {
+      bf16* f_hi = (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>();
+      bf16* f_lo = ((rsp || pair16) && R > 0) ? a_lo.as<bf16>() : nullptr;
+      const double fuse_bytes = double(Mo) * D * (16 + (w_i ? 8 : 0) + (xcur ? 4 : 0) + (f_hi ? 2 : 0) + (f_lo ? 2 : 0));
+      if (eval_wi_mean && eval_we_mean && !w_i)      // the evaluation loop's w_i.mean(-1) / w_e.mean(-1), train/ucf_test.py:124-131
+        IEF_PROF(KC_FUSE, fuse_bytes, fuse_rows(image_mu + out0 * D, event_mu + out0 * D, image_logvar + out0 * D, event_logvar + out0 * D,
+                 Mo, D, factor, eps, eval_wi_mean + out0, eval_we_mean + out0, xcur, f_hi, f_lo, num_sms, stream, r16 ? 1 : 0));
+      else
+        IEF_PROF(KC_FUSE, fuse_bytes, fuse(image_mu + out0 * D, event_mu + out0 * D, image_logvar + out0 * D, event_logvar + out0 * D, Mo * D,
+                 factor, eps, w_i ? w_i + out0 * D : nullptr, w_e ? w_e + out0 * D : nullptr, xcur, f_hi, f_lo, num_sms, stream, r16 ? 1 : 0));
+    }
     // iterative refinement (:146-149): x <- x - lambda * (W2 relu(W1 x + b1) + b2)
-    for (int i = 0; i < R; ++i) {
+    // fp16-pair stream with enough rows: ONE persistent kernel keeps each 256-row tile on chip for all R steps
+    bool chain = pair16 && D == kRefineDim && R <= kRefineMaxSteps && refine_contig && refine_fused != 0;
+    if (chain && refine_fused < 0) chain = refine_chain_preferred(Mo, num_sms);
+    if (chain) {
+      RefineChainArgs ra;
+      ra.x_hi = a_hi.p; ra.x_lo = a_lo.p; ra.w16 = ref1[0].w_h16;
+      for (int i = 0; i < R; ++i) { ra.b1[i] = ref1[i].b; ra.b2[i] = ref2[i].b; }
+      ra.steps = R; ra.lambda = lambda_ref; ra.M = Mo; ra.out_f32 = fused_out; ra.lo_scratch = h_hi.p;
+      IEF_CHECK(refine_chain_scratch_bytes(Mo) <= h_hi.bytes, "forward: refinement scratch too small");
+      IEF_PROF(KC_REFINE_FUSED, 4.0 * R * Mo * D * D, refine_chain(ra, num_sms, stream));
+    }
+    for (int i = 0; i < (chain ? 0 : R); ++i) {
       const bool last = (i == R - 1);
       float* xnext = last ? fused_out : x32.as<float>();
       if (fp32_plan) {
@@ -516,14 +548,14 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       }
     }
     // classifier (:150) stays fp32 in every plan
-    IEF_PROF(KC_CLASSIFIER, double(Mo) * D * 4, classifier(fused_out, Mo, D, cls_w, cls_b, logits + out0, scores ? scores + out0 : nullptr, num_sms, stream));
+    IEF_PROF(KC_CLASSIFIER, double(Mo) * D * 4, classifier(fused_out, Mo, D, cls_w, cls_b, logits + out0, scores ? scores + out0 : nullptr, num_sms, stream, status.as<int>()));
   }
   return IEFVAD_OK;
 }
 
 void Model::destroy() {
   DevBuf* all[] = {&params_f32, &params_hi, &params_lo, &params_h16, &x32, &y32, &a_hi, &a_lo, &h_hi, &h_lo,
-                   &qb, &kb, &vtb, &qkv32, &attn32, &h32, &inv_map};
+                   &qb, &kb, &vtb, &qkv32, &attn32, &h32, &inv_map, &items_dev, &aux_dev, &status};
   for (DevBuf* b : all) b->release();
 }
 

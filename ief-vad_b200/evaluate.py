@@ -82,6 +82,8 @@ class Evaluator:
         self.maxlen, self.repeat = maxlen, repeat
         self.rank, self.world, self.group = rank, world, process_group
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lengths = np.asarray(lengths, dtype=np.int64)
         self.classes = list(classes)
         n = len(self.lengths)
@@ -136,6 +138,7 @@ class Evaluator:
                                             np.zeros(0, dtype=np.int64), device=dev)
         self._chunk_valid_dev = torch.as_tensor(cv.astype(np.int32), device=dev)
         self._ragged = None
+        self.fell_back = False                 # a pass was redone under plan B after an fp16 overflow (on_overflow = "fallback")
         self.valid_rows_only = True
         self._img = self._ev = None
         self._pinned = None
@@ -177,19 +180,22 @@ class Evaluator:
         self._img = self._ev = None
 
     # ------------------------------------------------------------------ one evaluation pass
-    def local_scores(self, host_inputs: bool = False) -> torch.Tensor:
+    def local_scores(self, host_inputs: bool = False, extra: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         """Forward over all my chunks -> compacted sigmoid scores of my valid rows (device, fp32).  With host_inputs the
-        pinned host features go through the library's pipelined host-input forward (copy overlapped with compute)."""
+        pinned host features go through the library's pipelined host-input forward (copy overlapped with compute).
+        extra: optional compact outputs of the valid-rows forward (see `step(extras=...)`)."""
         packed = torch.empty(max(self.max_count, 1), dtype=torch.float32, device=self.device)
+        if extra and not (self.local_chunks and self.valid_rows_only and str(self.model.temporal.precision) != "fp32"):
+            raise RuntimeError("extras need the valid-rows evaluation forward (a tensor-core precision plan)")
         # (the fp32 FFMA plan has no valid-rows mode: it runs the full forward and compacts afterwards)
         if self.local_chunks and self.valid_rows_only and str(self.model.temporal.precision) != "fp32":
             if host_inputs and self._ragged is not None:
                 out = self.model.temporal.scores_ragged(self._ragged[0], self._ragged[1], self.device, self.maxlen,
                                                         self._chunk_valid, self._rowmap, self._chunk_start,
-                                                        self._chunk_valid_dev)
+                                                        self._chunk_valid_dev, extra=extra)
             else:
                 img, ev = self._pinned if host_inputs else (self._img, self._ev)
-                out = self.model.temporal.scores(img, ev, self.device, self._chunk_valid, self._rowmap)
+                out = self.model.temporal.scores(img, ev, self.device, self._chunk_valid, self._rowmap, extra=extra)
             self._keep = out["_keepalive"]
             packed[:self.my_rows].copy_(out["scores"])
             return packed
@@ -202,7 +208,8 @@ class Evaluator:
         return packed
 
     def gather(self, packed: torch.Tensor) -> torch.Tensor:
-        """The single collective: all ranks' padded score vectors -> list-order score vector on every rank."""
+        """The single collective: all ranks' padded score vectors -> list-order score vector on every rank.  (Also used
+        for the per-frame means of the fusion weights when `step(extras=...)` asks for them.)"""
         if self.world > 1:
             import torch.distributed as dist
             allv = torch.empty(self.world * max(self.max_count, 1), dtype=torch.float32, device=self.device)
@@ -225,6 +232,8 @@ class Evaluator:
     def finish(self, host_table: torch.Tensor) -> Dict[str, object]:
         """Wait for the stream and unpack a metrics table returned by `metrics_async`."""
         torch.cuda.current_stream(self.device).synchronize()
+        if not self.model.temporal.check_finite():          # range guard of the 16-bit plans (fp16 saturates at 65 504)
+            self.model.temporal._raise_overflow()
         table = host_table.numpy()
         res: Dict[str, object] = {"AUC": float(table[0, 0]), "AP": float(table[0, 1]),
                                   "ano_AUC": float(table[1, 0]),      # NaN when one label value only (:347-350)
@@ -238,10 +247,39 @@ class Evaluator:
     def metrics(self, scores: torch.Tensor) -> Dict[str, object]:
         return self.finish(self.metrics_async(scores))
 
-    def step(self, host_inputs: bool = False, with_metrics: bool = True, sync: bool = True) -> Dict[str, object]:
+    def step(self, host_inputs: bool = False, with_metrics: bool = True, sync: bool = True,
+             extras: Sequence[str] = ()) -> Dict[str, object]:
         """One evaluation pass.  With sync=False nothing waits for the device: the returned dict holds the device
-        score vector and, under "pending", the pinned metrics table to hand to `finish()` later."""
-        scores = self.gather(self.local_scores(host_inputs))
+        score vector and, under "pending", the pinned metrics table to hand to `finish()` later.
+
+        extras - what the reference's loop collects per class besides the scores (train/ucf_test.py:124-144), kept on the
+        device: "w_mean" adds "wi_mean" / "we_mean" ([total rows] in list order on every rank: w_i.mean(-1), w_e.mean(-1)
+        of every frame, reduced inside the fusion kernel) and "classwise_wi" / "classwise_we" (class key -> the frames of
+        that class's videos, list order); "wide" adds this rank's compact [my rows, D] "fused", "image_mu", "event_mu"
+        (rows of `self.mine` videos back to back) and "classwise_fused" / "classwise_image_mu" / "classwise_event_mu" for
+        the classes of this rank's videos."""
+        extra: Dict[str, torch.Tensor] = {}
+        unknown = set(extras) - {"w_mean", "wide"}
+        if unknown:
+            raise KeyError(f"unknown extras {sorted(unknown)}; choose from 'w_mean', 'wide'")
+        if "w_mean" in extras:
+            for k in ("wi_mean", "we_mean"):
+                extra[k] = torch.zeros(max(self.max_count, 1), dtype=torch.float32, device=self.device)
+        if "wide" in extras:
+            for k in ("fused", "image_mu", "event_mu"):
+                extra[k] = torch.empty((self.my_rows, self.model.embed_dim), dtype=torch.float32, device=self.device)
+        call_extra = {k: (v[:self.my_rows] if v.dim() == 1 else v) for k, v in extra.items()}
+        scores = self.gather(self.local_scores(host_inputs, call_extra or None))
+        temporal = self.model.temporal
+        if sync and getattr(temporal, "on_overflow", "raise") == "fallback" and str(temporal.precision) not in ("B", "fp32"):
+            if not temporal.check_finite():                  # an fp16 operand overflowed: redo the pass in bf16 (plan B)
+                keep = temporal.precision
+                temporal.precision = "B"
+                try:
+                    scores = self.gather(self.local_scores(host_inputs))
+                finally:
+                    temporal.precision = keep
+                self.fell_back = True
         res: Dict[str, object] = {}
         if with_metrics:
             pending = self.metrics_async(scores)
@@ -250,7 +288,32 @@ class Evaluator:
             else:
                 res["pending"] = pending
         res["scores"] = scores
+        if "w_mean" in extras:
+            for k, ck in (("wi_mean", "classwise_wi"), ("we_mean", "classwise_we")):
+                res[k] = self.gather(extra[k])
+                res[ck] = {name: res[k][idx] for name, idx in self._class_rows().items()}
+        if "wide" in extras:
+            local = self._class_rows(local=True)
+            for k in ("fused", "image_mu", "event_mu"):
+                res[k] = extra[k]
+                res["classwise_" + k] = {name: extra[k][idx] for name, idx in local.items()}
         return res
+
+    def _class_rows(self, local: bool = False) -> Dict[str, torch.Tensor]:
+        """class key -> device index vector of that class's frames: into the list-order vectors, or (local=True) into this
+        rank's compact rows (videos of `self.mine` back to back)."""
+        cache = self.__dict__.setdefault("_class_rows_cache", {})
+        if local not in cache:
+            vids = self.mine if local else range(len(self.lengths))
+            if local:
+                start = dict(zip(self.mine, np.concatenate([[0], np.cumsum(self.lengths[self.mine])])[:-1])) if len(self.mine) else {}
+            else:
+                start = dict(enumerate(self.global_off))
+            rows: Dict[str, list] = {}
+            for v in vids:
+                rows.setdefault(self.classes[v], []).append(np.arange(int(start[v]), int(start[v] + self.lengths[v])))
+            cache[local] = {k: torch.as_tensor(np.concatenate(a).astype(np.int64), device=self.device) for k, a in rows.items()}
+        return cache[local]
 
     def step_breakdown(self, reps: int = 5, host_inputs: bool = False) -> Dict[str, float]:
         """Where a step's device time goes: forward over my chunks | the single collective (+ re-ordering into list

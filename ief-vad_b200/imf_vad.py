@@ -20,6 +20,14 @@ from . import _lib
 _MODALITIES = ("image", "event")
 
 
+def _norm_device(device) -> torch.device:
+    """torch.device with an explicit index ("cuda" -> "cuda:<current>"), so it compares equal to tensor.device."""
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
 class MultiModal_Fusion_Attn_Iter(nn.Module):
     """Parameter layout of model/imf_vad.py:69-107; forward of :109-161 on the GPU."""
 
@@ -38,6 +46,13 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         self.precision = os.environ.get("IEFVAD_PLAN", "HH")
         # valid-rows evaluation forward: compute the identical zero-pad rows of a chunk once (pad de-duplication)
         self.pad_dedup = True
+        # refinement chain as one persistent kernel: None = when the batch is large enough (library default), False /
+        # True = never / always (both forms produce identical bits; iefvad_model_set_option "refine_fused")
+        self.refine_fused = None
+        # range guard of the 16-bit plans: "raise" (default) = check_finite() / Evaluator.finish() raise when a forward
+        # produced a non-finite logit; "fallback" = the Evaluator re-runs the pass under the bf16 plan "B"
+        self.on_overflow = os.environ.get("IEFVAD_ON_OVERFLOW", "raise")
+        self.check_every_forward = os.environ.get("IEFVAD_CHECK", "0") not in ("", "0")
 
         # nn.MultiheadAttention / LayerNorm / Linear instances are used purely as parameter containers: they give
         # the reference's state_dict keys and consume the RNG exactly like the reference constructor does
@@ -95,9 +110,62 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             _lib.check(_lib.lib.iefvad_model_set_max_rows(self._handle, max_rows))
         return self._handle
 
+    def refresh_weights(self) -> None:
+        """Force a re-upload of every parameter on the next forward.  The automatic check compares (storage address,
+        tensor version) per parameter, which sees load_state_dict, optimizer steps, .to() and every in-place op on the
+        parameter itself - but NOT writes through `.data` (p.data.mul_(), EMA updates on .data), which bypass the
+        version counter: call this after such an update."""
+        self._uploaded = {}
+
+    def check_finite(self) -> bool:
+        """Range guard (synchronises): True when every logit produced since the last check was finite.  fp16 operands
+        saturate at 65 504 where the reference's fp32 does not; an overflow anywhere upstream reaches the classifier
+        as inf / NaN and sets a device flag (include/iefvad.h, iefvad_model_check_finite)."""
+        if self._handle is None:
+            return True
+        import ctypes as C
+        flag = C.c_int(0)
+        with torch.cuda.device(self._handle_device):
+            _lib.check(_lib.lib.iefvad_model_check_finite(self._handle, C.byref(flag),
+                                                          torch.cuda.current_stream(self._handle_device).cuda_stream))
+        return flag.value == 0
+
+    def _raise_overflow(self):
+        raise FloatingPointError(
+            f"IEF-VAD B200 path: precision plan {self.precision!r} produced non-finite logits - a 16-bit operand left "
+            "the fp16 range (65 504).  Re-run with model.temporal.precision = 'B' (bf16 operands, fp32's exponent range) "
+            "or 'fp32'.")
+
+    def _set_eval_outputs(self, h: int, extra: Optional[Dict[str, torch.Tensor]], n_rows: int, device) -> None:
+        """Register (or clear, extra=None) the optional outputs of the evaluation forward: what the reference's loop
+        derives per frame besides the score (train/ucf_test.py:124-144).  Keys: "wi_mean", "we_mean" [rows] and
+        "fused", "image_mu", "event_mu" [rows, D] - fp32 device tensors of the caller (compact in valid-rows mode)."""
+        ptrs = [0] * 5
+        if extra:
+            for i, (key, width) in enumerate((("wi_mean", 1), ("we_mean", 1), ("fused", self.embed_dim),
+                                              ("image_mu", self.embed_dim), ("event_mu", self.embed_dim))):
+                t = extra.get(key)
+                if t is None:
+                    continue
+                if (not t.is_cuda or t.device != device or t.dtype != torch.float32 or not t.is_contiguous()
+                        or t.numel() != n_rows * width):
+                    raise RuntimeError(f"extra output {key!r} must be a contiguous fp32 tensor of {n_rows * width} "
+                                       f"elements on {device}")
+                ptrs[i] = t.data_ptr()
+            unknown = set(extra) - {"wi_mean", "we_mean", "fused", "image_mu", "event_mu"}
+            if unknown:
+                raise KeyError(f"unknown extra outputs {sorted(unknown)}")
+        _lib.check(_lib.lib.iefvad_model_set_eval_outputs(h, *ptrs))
+
+    def _apply_options(self, h: int) -> None:
+        mode = -1 if self.refine_fused is None else (int(self.refine_fused) if not isinstance(self.refine_fused, bool)
+                                                     else int(self.refine_fused))
+        _lib.check(_lib.lib.iefvad_model_set_option(h, b"refine_fused", mode))
+
     def _sync_params(self, handle: int, device: torch.device, stream: int) -> None:
         """Upload parameters whose storage or version changed since the last forward (load_state_dict,
-        optimizer steps, .to())."""
+        optimizer steps, .to(), in-place ops on the parameter); see `refresh_weights` for writes through `.data`."""
+        self._apply_options(handle)
         for name, p in self.named_parameters():
             tag = (p.data_ptr(), p._version)
             if self._uploaded.get(name) == tag:
@@ -163,6 +231,8 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
                 logits = torch.empty((B, T, 1), dtype=torch.float32, device=device)
                 scores = torch.empty((B, T), dtype=torch.float32, device=device) if with_scores else None
                 launch(img, ev, wide, logits, scores)
+        if self.check_every_forward and not self.check_finite():
+            self._raise_overflow()
         out = {
             "fused": wide[0], "logits": logits, "image_mu": wide[1], "event_mu": wide[2],
             "image_logvar": wide[3], "event_logvar": wide[4], "w_i": wide[5], "w_e": wide[6],
@@ -180,7 +250,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         limit = int(os.environ.get("IEFVAD_GRAPH_ROWS", "2048") or 0)
         if B * T > limit or torch.cuda.is_current_stream_capturing():
             return None
-        key = (str(device), B, T, img.dtype, plan, bool(with_scores))
+        key = (str(device), B, T, img.dtype, plan, bool(with_scores), self.refine_fused)
         cache = self.__dict__.setdefault("_graphs", {})
         entry = cache.get(key)
         if entry is False:
@@ -222,8 +292,8 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         return (out[:n_wide].view(7, B, T, D), out[n_wide:n_wide + B * T].view(B, T, 1),
                 out[n_wide + B * T:].view(B, T) if with_scores else None)
 
-    def scores(self, img: torch.Tensor, ev: torch.Tensor, device=None, valid_lengths=None, rowmap=None
-               ) -> Dict[str, torch.Tensor]:
+    def scores(self, img: torch.Tensor, ev: torch.Tensor, device=None, valid_lengths=None, rowmap=None,
+               extra: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Evaluation forward (iefvad_model_forward_scores): device `logits` / `scores` only.
 
         img / ev: [B, T, D] on the device, or on the HOST (ideally pinned; `device` then names the GPU) - host inputs
@@ -242,7 +312,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         on_host = not img.is_cuda
         if on_host != (not ev.is_cuda):
             raise RuntimeError("img and ev must both be on the host or both on the device")
-        device = torch.device(device) if on_host else img.device
+        device = _norm_device(device) if on_host else img.device
         if on_host and device.type != "cuda":
             raise RuntimeError("host inputs need the target CUDA device")
         img, ev = img.contiguous(), ev.contiguous()
@@ -268,15 +338,20 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             _lib.check(_lib.lib.iefvad_model_set_pad_dedup(h, 1 if self.pad_dedup else 0))
             logits = torch.empty(max(n_out, 1), dtype=torch.float32, device=device)[:n_out]
             scores = torch.empty(max(n_out, 1), dtype=torch.float32, device=device)[:n_out]
-            _lib.check(_lib.lib.iefvad_model_forward_scores(
-                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], int(on_host), B, T, lens_ptr, _lib.ptr(rowmap),
-                logits.data_ptr(), scores.data_ptr(), stream))
+            self._set_eval_outputs(h, extra, n_out, device)
+            try:
+                _lib.check(_lib.lib.iefvad_model_forward_scores(
+                    h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], int(on_host), B, T, lens_ptr, _lib.ptr(rowmap),
+                    logits.data_ptr(), scores.data_ptr(), stream))
+            finally:
+                if extra:
+                    self._set_eval_outputs(h, None, 0, device)
         if valid_lengths is None:
             logits, scores = logits.view(B, T, 1), scores.view(B, T)
         return {"logits": logits, "scores": scores, "_keepalive": keep}
 
     def scores_ragged(self, img_packed: torch.Tensor, ev_packed: torch.Tensor, device, T: int, valid_lengths, rowmap,
-                      chunk_start, chunk_valid) -> Dict[str, torch.Tensor]:
+                      chunk_start, chunk_valid, extra: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Evaluation forward from RAGGED host features (iefvad_model_forward_scores_ragged): img_packed / ev_packed are
         HOST (pinned) [sum len, D] tensors holding only the valid rows of the zero-padded [T, D] chunks, chunk after
         chunk; the chunk / pad rule of data/tools.py:100-114 is applied on the device while ingesting.  valid_lengths:
@@ -291,7 +366,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             raise RuntimeError(f"packed features must be [{n}, {self.embed_dim}] float32 / float16 / bfloat16")
         if any(v < 0 or v > T for v in lens):
             raise RuntimeError("valid lengths must lie in [0, T]")
-        device = torch.device(device)
+        device = _norm_device(device)
         for t, dt, cnt in ((rowmap, torch.int32, n), (chunk_start, torch.int64, B), (chunk_valid, torch.int32, B)):
             if not t.is_cuda or t.dtype != dt or t.numel() != cnt:
                 raise RuntimeError("rowmap / chunk_start / chunk_valid must be device tensors (int32 [sum len], int64 [B], int32 [B])")
@@ -308,9 +383,14 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             _lib.check(_lib.lib.iefvad_model_set_pad_dedup(h, 1 if self.pad_dedup else 0))
             logits = torch.empty(max(n, 1), dtype=torch.float32, device=device)[:n]
             scores = torch.empty(max(n, 1), dtype=torch.float32, device=device)[:n]
-            _lib.check(_lib.lib.iefvad_model_forward_scores_ragged(
-                h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], B, T, C.cast(arr, C.c_void_p), rowmap.data_ptr(),
-                chunk_start.data_ptr(), chunk_valid.data_ptr(), logits.data_ptr(), scores.data_ptr(), stream))
+            self._set_eval_outputs(h, extra, n, device)
+            try:
+                _lib.check(_lib.lib.iefvad_model_forward_scores_ragged(
+                    h, img.data_ptr(), ev.data_ptr(), codes[img.dtype], B, T, C.cast(arr, C.c_void_p), rowmap.data_ptr(),
+                    chunk_start.data_ptr(), chunk_valid.data_ptr(), logits.data_ptr(), scores.data_ptr(), stream))
+            finally:
+                if extra:
+                    self._set_eval_outputs(h, None, 0, device)
         return {"logits": logits, "scores": scores, "_keepalive": (img, ev, arr, rowmap, chunk_start, chunk_valid)}
 
     def scores_from_host(self, img_host: torch.Tensor, ev_host: torch.Tensor, device) -> Dict[str, torch.Tensor]:

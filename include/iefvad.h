@@ -70,6 +70,15 @@ int iefvad_model_set_param(iefvad_model* m, const char* key, const float* data, 
 
 int iefvad_model_set_plan(iefvad_model* m, int plan);
 int iefvad_model_get_plan(const iefvad_model* m);
+/* Tuning / test knobs by name.  "refine_fused": the refinement chain (model/imf_vad.py:146-149) as ONE persistent kernel
+ * whose hidden activations never leave the SM: -1 = when the batch fills the CTA pairs (default), 0 = never (two tcgen05
+ * GEMM launches per step), 1 = always.  Both forms give identical bits. */
+int iefvad_model_set_option(iefvad_model* m, const char* name, int64_t value);
+/* Range guard of the 16-bit operand plans (fp16 saturates at 65 504; the reference computes in fp32): every forward
+ * ORs bit 0 of a device flag when it produced a non-finite logit - an operand that overflowed anywhere upstream reaches
+ * the classifier as inf / NaN.  This call copies the flag to *nonfinite_host, clears it and SYNCHRONISES the stream.
+ * Callers re-run with a bf16 plan (IEFVAD_PLAN_B, fp32's exponent range) or IEFVAD_PLAN_FP32 when it is set. */
+int iefvad_model_check_finite(iefvad_model* m, int* nonfinite_host, void* stream);
 /* rows per internal slab (bounds the activation workspace, ~18 KB per row); default 262144 */
 int iefvad_model_set_max_rows(iefvad_model* m, int64_t max_rows);
 
@@ -129,6 +138,15 @@ int iefvad_model_forward_scores_ragged(iefvad_model* m, const void* img_packed_h
                                        int in_dtype, int64_t B, int64_t T, const int64_t* valid_len_host,
                                        const int32_t* rowmap, const int64_t* chunk_start, const int32_t* chunk_valid,
                                        float* logits, float* scores, void* stream);
+
+/* What the reference's evaluation loop derives from the forward besides the scores (train/ucf_test.py:124-144):
+ * `w_i.mean(dim=-1)`, `w_e.mean(dim=-1)` per frame and the frames' `fused`, `image_mu`, `event_mu` rows.  Registers
+ * optional DEVICE output buffers for the following iefvad_model_forward_scores[_ragged] calls (sticky; NULL = not
+ * wanted; all-NULL restores the default): wi_mean / we_mean [rows] (both or neither; the row reduction is fused into the
+ * fusion kernel - 8 bytes per frame instead of the two [rows, embed_dim] weight tensors), fused / image_mu / event_mu
+ * [rows, embed_dim], where rows = sum of the valid lengths in valid-rows mode (compact, like logits / scores), else B * T. */
+int iefvad_model_set_eval_outputs(iefvad_model* m, float* wi_mean, float* we_mean, float* fused, float* image_mu,
+                                  float* event_mu);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone operators (device pointers) - the same kernels the forward uses, exposed for parity tests
@@ -285,12 +303,13 @@ uint64_t iefvad_alloc_generation(void);
 void iefvad_add_launches(uint64_t n);
 
 /* Per-kernel-class device timing of the model forward with CUDA events on the launching stream.
- * classes (IEFVAD_PROFILE_CLASSES = 12): 0 gemm_tc QKV in-projection, 1 attn_tc, 2 layernorm, 3 fuse, 4 classifier,
+ * classes (IEFVAD_PROFILE_CLASSES = 15): 0 gemm_tc QKV in-projection, 1 attn_tc, 2 layernorm, 3 fuse, 4 classifier,
  * 5 ingest, 6 gemm_simt, 7 attn_simt, 8 gemm_tc out-projection, 9 gemm_tc heads, 10 gemm_tc refinement Linear 1
- * (ReLU), 11 gemm_tc refinement Linear 2 (residual), 12 valid-row gather.  iefvad_profile_read synchronises, fills ms / work (algorithmic
- * FLOPs for the GEMM and attention classes, algorithmic bytes otherwise) / launches (arrays of 13) for everything
+ * (ReLU), 11 gemm_tc refinement Linear 2 (residual), 12 valid-row gather, 13 fused refinement chain, 14 heads + fusion.
+ * iefvad_profile_read synchronises, fills ms / work (executed
+ * FLOPs for the GEMM and attention classes, bytes moved otherwise) / launches (arrays of IEFVAD_PROFILE_CLASSES) for everything
  * recorded since the last read, and clears the record. */
-#define IEFVAD_PROFILE_CLASSES 13
+#define IEFVAD_PROFILE_CLASSES 15
 int iefvad_profile_enable(int on);
 int iefvad_profile_read(double* ms, double* work, int64_t* launches);
 

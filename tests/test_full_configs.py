@@ -160,6 +160,43 @@ def test_config2_default_evaluator_path_full_size(gpu_model, inputs):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("inputs", ["device_chunks", "host_ragged"])
+def test_config2_evaluator_extras_match_the_reference_loop(gpu_model, inputs):
+    """Row N1: what the reference's loop collects per class besides the scores (train/ucf_test.py:124-144) - the per-frame
+    means of the fusion weights (reduced inside the fusion kernel) and the frames' fused / image_mu / event_mu rows - from
+    the valid-rows evaluation forward, against the reference's own values on the full bench workload."""
+    m, synth = gpu_model
+    z = load_golden("config2_ucf.npz")
+    m.temporal.precision = "HH"
+    ev, fi, fe = _evaluator(m, synth, "ucf")
+    with torch.no_grad():
+        if inputs == "device_chunks":
+            ev.set_device_features(ev.chunk_features(fi), ev.chunk_features(fe))
+            res = ev.step(extras=("w_mean", "wide"))
+            plain = ev.step()
+        else:
+            ev.set_host_ragged(fi, fe)
+            res = ev.step(host_inputs=True, extras=("w_mean", "wide"))
+            plain = ev.step(host_inputs=True)
+    assert torch.equal(res["scores"], plain["scores"])           # asking for the extras does not change a bit of the scores
+    assert np.max(np.abs(res["wi_mean"].cpu().numpy() - z["wi_mean"])) < 1e-4
+    assert np.max(np.abs(res["we_mean"].cpu().numpy() - z["we_mean"])) < 1e-4
+    T = z["lengths"]
+    off = np.concatenate([[0], np.cumsum(T)])[:-1]
+    rows = torch.as_tensor(off, device="cuda")
+    for j, k in enumerate(("fused", "image_mu", "event_mu")):
+        assert res[k].shape == (int(T.sum()), 768)
+        assert O.max_norm_err(res[k][rows].cpu().numpy(), z["first_rows"][:, j]) < 1e-3, k
+    # per class, in list order - the reference's classwise_wi[cls] lists concatenated
+    classes = [str(c) for c in z["classes"]]
+    for key in ("Abuse", "Normal", "Vandalism"):
+        idx = np.concatenate([np.arange(off[v], off[v] + T[v]) for v in range(len(T)) if classes[v] == key])
+        assert np.max(np.abs(res["classwise_wi"][key].cpu().numpy() - z["wi_mean"][idx])) < 1e-4
+        assert res["classwise_fused"][key].shape == (idx.size, 768)
+        assert torch.equal(res["classwise_fused"][key], res["fused"][torch.as_tensor(idx, device="cuda")])
+
+
+@pytest.mark.gpu
 def test_config2_drop_in_module_forward_all_eight_tensors_ucf_shape(gpu_model):
     """MMFMIL.forward on the [465, 256, 768] chunk batch of the bench workload: scores of all valid rows, the w_i / w_e
     row means the reference's loop derives (train/ucf_test.py:124-131) and the first row of fused / mu per video."""
