@@ -95,6 +95,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// smem (shared-space address) -> global tensor store; rows past the tensor bound are clipped
+__device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -139,7 +151,8 @@ struct RefineParams {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                    const __grid_constant__ CUtensorMap tmW2, const RefineParams p) {
+                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmSH,
+                    const __grid_constant__ CUtensorMap tmSL, const __grid_constant__ CUtensorMap tmSO, const RefineParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -162,6 +175,9 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmSH);
+    tma_prefetch_desc(&tmSL);
+    tma_prefetch_desc(&tmSO);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -304,13 +320,25 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     long long w_acc = 0, w_a2f = 0;
     const long long t_begin = clock64();
     uint32_t n_acc = 0, n_a2 = 0;
+    int publish_t = -1;                           // tile whose step this warp has finished but not yet published
+    auto publish = [&]() {                        // this warp's share of a step of tile publish_t is in global memory
+      if (publish_t >= 0 && lane == 0) {
+        bulk_wait_all<0>();                       // the tensor stores have been performed, not just read out of Ob
+        fence_proxy_async_all();
+        __threadfence();
+        atomicAdd(p.done + publish_t, 1);
+      }
+      publish_t = -1;
+    };
     for (int u = pair; u < units; u += npairs) {
       const int s = u / T, t = u - s * T;
       const bool last = s == R - 1;
       const float* b2 = p.b2[s];
-      if (s > 0) {      // unit (s - 1, t) has written this tile's (hi, lo): acquire it for the copies below (the producer
-        if (lane == 0)  // thread does the same for its TMA loads)
-          while (ld_acquire_gpu(p.done + t) < 16 * s) __nanosleep(32);
+      if (s > 0) {      // unit (s - 1, t) must have written this tile's (hi, lo) before the copies below read them.  Its writer
+        // fenced before bumping the counter and the copies read L2 (cp.async.cg) behind a branch on the counter, so a
+        // relaxed poll is enough (an acquire costs a MEMBAR + L1 invalidation per warp and unit: 13 % of the stall samples)
+        if (lane == 0)
+          while (ld_relaxed_gpu(p.done + t) < 16 * s) __nanosleep(32);
         __syncwarp();
       }
       // global side of the staging tiles: instruction j moves rows 4 j + (lane >> 3), 16-byte chunk lane & 7 of this warp's
@@ -357,6 +385,7 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_tmem(lead(upfree));
+        if (c == 0) publish();                    // the previous unit's results (nothing waits on this warp meanwhile)
         pack(b1 + c * 256 + 128 + 64 * hf, pk + 32);
         const uint32_t tl = tlane + uint32_t(128 * c + 64 * hf);
         tmem_ld32(tl, v);
@@ -380,16 +409,7 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll 1
       for (int n = 0; n < NCH2; ++n) {
         const int col0 = n * 128 + 64 * hf;
-        cp_async_wait_all();
-        __syncwarp();
-        uint4 h4[8], l4[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {            // my row's 64 columns of hi and lo
-          h4[c] = lds128(Hb + sw128(lane, c));
-          l4[c] = lds128(Lb + sw128(lane, c));
-        }
-        __syncwarp();                            // every lane holds its row: Hb / Lb may take the next chunk
-        if (n + 1 < NCH2) fetch(n + 1);          // in flight while this chunk is computed and written out
+        // the accumulator first: the tensor pipe idles until every warp of the pair has read it out
         TWAIT(w_a2f, mbar_wait(a2full, n_a2 & 1u));
         ++n_a2;
         tc_fence_after();
@@ -401,6 +421,16 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_tmem(lead(a2free));
+        cp_async_wait_all();
+        __syncwarp();
+        uint4 h4[8], l4[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {            // my row's 64 columns of hi and lo
+          h4[c] = lds128(Hb + sw128(lane, c));
+          l4[c] = lds128(Lb + sw128(lane, c));
+        }
+        __syncwarp();                            // every lane holds its row: Hb / Lb may take the next chunk
+        if (n + 1 < NCH2) fetch(n + 1);          // in flight while this chunk is computed and written out
         const float4* bp = reinterpret_cast<const float4*>(b2 + col0);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -429,9 +459,11 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             l4[g] = make_uint4(nl[0], nl[1], nl[2], nl[3]);
           }
         }
-        // out through Ob, one 4 KB tile at a time: my row in, whole 128-byte rows out
+        // out through Ob, one 4 KB tile at a time: my row in (swizzled like a TMA box), one bulk tensor store out
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
+          if (lane == 0) bulk_wait_read<0>();    // the previous store has finished reading Ob
+          __syncwarp();
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 w;
@@ -440,25 +472,25 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                                 __float_as_uint(v[32 * half + 4 * c + 2]), __float_as_uint(v[32 * half + 4 * c + 3]));
             sts128(Ob + sw128(lane, c), w);
           }
+          fence_proxy_async_smem();
           __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const long long rr = wrow0 + 4 * j + crow;
-            const uint4 w = lds128(Ob + sw128(4 * j + crow, cchk));
-            if (rr < p.M) {
-              if (!last) *reinterpret_cast<uint4*>((half ? p.x_lo : p.x_hi) + rr * D + col0 + 8 * cchk) = w;
-              else *reinterpret_cast<uint4*>(p.out + rr * D + col0 + 32 * half + 4 * cchk) = w;
-            }
+          if (lane == 0) {
+            if (!last) tma_store_2d_s(half ? &tmSL : &tmSH, Ob, col0, int(wrow0));
+            else tma_store_2d_s(&tmSO, Ob, col0 + 32 * half, int(wrow0));
+            bulk_commit();
           }
-          __syncwarp();
         }
       }
-      if (!last) {                                // publish: this warp's share of step s of tile t is in global memory
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(p.done + t, 1);
+      // Published after the next unit's first accumulator read-out (waiting for the stores here would delay it) - but only
+      // when that next unit cannot depend on this one: with more tiles than pairs its predecessor (s, t') lies before this
+      // unit in the global order; with T <= npairs it may BE this unit, and deferring would deadlock the pair on itself.
+      if (!last) {
+        publish_t = t;
+        if (T <= npairs) publish();
       }
     }
+    publish();
+    if (lane == 0) bulk_wait_all<0>();            // Ob must outlive the last stores
     if (tr && lane == 0) { p.trace[12] = clock64() - t_begin; p.trace[13] = w_acc; p.trace[14] = w_a2f; }
   }
 
@@ -486,8 +518,12 @@ int refine_chain(const RefineChainArgs& a, int num_sms, cudaStream_t stream) {
   IEF_CHECK(a.x_hi && a.x_lo && a.w16 && a.out_f32 && a.lo_scratch, "refine_chain: null argument");
   IEF_CHECK(a.steps >= 1 && a.steps <= kRefineMaxSteps, "refine_chain: 1 <= steps <= %d", kRefineMaxSteps);
   IEF_CHECK(a.M > 0 && a.M < (1LL << 31), "refine_chain: bad row count %lld", a.M);
-  CUtensorMap tx, tw1, tw2;
+  CUtensorMap tx, tw1, tw2, tsh, tsl, tso;
   IEF_TRY(make_tmap_2d(&tx, a.x_hi, D, uint64_t(a.M), uint64_t(D) * 2, BK, BM));
+  // epilogue stores: 32 rows x 128 bytes per warp and box
+  IEF_TRY(make_tmap_2d(&tsh, a.x_hi, D, uint64_t(a.M), uint64_t(D) * 2, 64, 32));
+  IEF_TRY(make_tmap_2d(&tsl, a.x_lo, D, uint64_t(a.M), uint64_t(D) * 2, 64, 32));
+  IEF_TRY(make_tmap_2d(&tso, a.out_f32, D, uint64_t(a.M), uint64_t(D) * 4, 32, 32, TM_F32, TM_SWIZZLE_128B));
   IEF_TRY(make_tmap_3d(&tw1, a.w16, D, D, uint64_t(2 * a.steps), uint64_t(D) * 2, uint64_t(D) * D * 2, BK, 128, 1));
   IEF_TRY(make_tmap_3d(&tw2, a.w16, D, D, uint64_t(2 * a.steps), uint64_t(D) * 2, uint64_t(D) * D * 2, BK, 64, 1));
   RefineParams p;
@@ -522,7 +558,7 @@ int refine_chain(const RefineChainArgs& a, int num_sms, cudaStream_t stream) {
     IEF_CUDA(cudaFuncSetAttribute(refine_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
     attr_set = true;
   }
-  refine_chain_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tx, tw1, tw2, p);
+  refine_chain_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tx, tw1, tw2, tsh, tsl, tso, p);
   IEF_CUDA(cudaGetLastError());
   count_launches(1);
   if (p.trace) {
