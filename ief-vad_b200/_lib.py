@@ -62,6 +62,16 @@ _SIGS = {
     "iefvad_transformer": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "iefvad_process_split": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _i, _vp]),
     "iefvad_process_feat": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _i, _vp]),
+    "iefvad_attention_train_fwd": (_i, [_vp, _i64, _i64, _i, _i, _f, C.c_uint64, _vp, _vp, _vp]),
+    "iefvad_attention_train_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _f, C.c_uint64, _vp, _vp]),
+    "iefvad_layernorm_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
+    "iefvad_colsum": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "iefvad_fuse_bwd": (_i, [_vp] * 11 + [_i64, _f, _f] + [_vp] * 5),
+    "iefvad_relu_bwd": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "iefvad_axpy": (_i, [_vp, _vp, _f, _i64, _vp]),
+    "iefvad_outer": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "iefvad_transpose": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
+    "iefvad_clas2_bwd": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp]),
     "iefvad_bench_gemm": (_i, [_i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "iefvad_launch_count": (C.c_uint64, []),
     "iefvad_alloc_generation": (C.c_uint64, []),

@@ -16,6 +16,7 @@
 #include "model.cuh"
 #include "rank.cuh"
 #include "shaping.cuh"
+#include "train.cuh"
 
 namespace iefvad {
 const char* last_error();
@@ -673,6 +674,94 @@ void iefvad_add_launches(uint64_t n) { count_launches(int(n)); }
 int iefvad_profile_enable(int on) {
   profiler().on = on != 0;
   return IEFVAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ training step (N3)
+
+int iefvad_attention_train_fwd(const float* qkv, int64_t B, int64_t T, int heads, int head_dim, float p_drop, uint64_t seed,
+                               float* out, float* lse, void* stream) {
+  IEF_CHECK(qkv && out && lse, "iefvad_attention_train_fwd: null argument");
+  IEF_CHECK(B >= 0 && B < 65536 && T >= 0 && T < (1 << 24), "iefvad_attention_train_fwd: bad B / T");
+  return attn_train_fwd(qkv, int(B), int(T), heads, head_dim, p_drop, seed, out, lse, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int64_t B, int64_t T,
+                               int heads, int head_dim, float p_drop, uint64_t seed, float* dqkv, void* stream) {
+  IEF_CHECK(qkv && out && dout && lse && dqkv, "iefvad_attention_train_bwd: null argument");
+  IEF_CHECK(B >= 0 && B < 65536 && T >= 0 && T < (1 << 24), "iefvad_attention_train_bwd: bad B / T");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  Scratch sc(st);
+  void* delta = nullptr;
+  IEF_TRY(sc.get(&delta, size_t(B) * heads * T * 4));
+  return attn_train_bwd(qkv, out, dout, lse, int(B), int(T), heads, head_dim, p_drop, seed, static_cast<float*>(delta), dqkv, sms, st);
+}
+
+int iefvad_layernorm_bwd(const float* x, const float* weight, const float* dy, int64_t rows, int dim, float eps, float* dx,
+                         float* dweight, float* dbias, void* stream) {
+  IEF_CHECK(x && weight && dy && dx && dweight && dbias, "iefvad_layernorm_bwd: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  Scratch sc(st);
+  void* scratch = nullptr;
+  IEF_TRY(sc.get(&scratch, (size_t(2) * rows + size_t(2) * train_colsum_blocks(rows, sms) * dim) * 4));
+  return layernorm_bwd(x, weight, dy, rows, dim, eps, dx, dweight, dbias, static_cast<float*>(scratch), sms, st);
+}
+
+int iefvad_colsum(const float* a, const float* row_weight, int64_t rows, int dim, float* out, void* stream) {
+  IEF_CHECK(a && out, "iefvad_colsum: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  Scratch sc(st);
+  void* scratch = nullptr;
+  IEF_TRY(sc.get(&scratch, size_t(2) * train_colsum_blocks(rows, sms) * dim * 4));
+  return colsum(a, row_weight, rows, dim, out, static_cast<float*>(scratch), sms, st);
+}
+
+int iefvad_fuse_bwd(const float* mu_i, const float* mu_e, const float* logvar_i, const float* logvar_e, const float* g_fused,
+                    const float* g_wi, const float* g_we, const float* g_mu_i, const float* g_mu_e, const float* g_logvar_i,
+                    const float* g_logvar_e, int64_t n, float factor, float epsilon, float* d_mu_i, float* d_mu_e,
+                    float* d_logvar_i, float* d_logvar_e, void* stream) {
+  IEF_CHECK(mu_i && mu_e && logvar_i && logvar_e && d_mu_i && d_mu_e && d_logvar_i && d_logvar_e, "iefvad_fuse_bwd: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return fuse_bwd(mu_i, mu_e, logvar_i, logvar_e, g_fused, g_wi, g_we, g_mu_i, g_mu_e, g_logvar_i, g_logvar_e, n, factor, epsilon,
+                  d_mu_i, d_mu_e, d_logvar_i, d_logvar_e, sms, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_relu_bwd(const float* dh, const float* h, int64_t n, float* out, void* stream) {
+  IEF_CHECK(dh && h && out, "iefvad_relu_bwd: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return relu_bwd(dh, h, n, out, sms, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {
+  IEF_CHECK(y && x, "iefvad_axpy: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return axpy(y, x, alpha, n, sms, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_outer(const float* a, const float* w, int64_t rows, int dim, float* out, void* stream) {
+  IEF_CHECK(a && w && out, "iefvad_outer: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return outer(a, w, rows, dim, out, sms, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_transpose(const float* src, int64_t rows, int cols, float* dst, int64_t ld_dst, void* stream) {
+  IEF_CHECK(src && dst, "iefvad_transpose: null argument");
+  return transpose_f32(src, rows, cols, dst, ld_dst, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_clas2_bwd(const float* logits, const float* means, const float* labels, int64_t label_stride, const int32_t* idx,
+                     int64_t B, int64_t T, int kmax, const float* g_loss, float* dlogits, void* stream) {
+  IEF_CHECK(logits && means && labels && idx && dlogits, "iefvad_clas2_bwd: null argument");
+  return clas2_bwd(logits, means, labels, label_stride, idx, int(B), int(T), kmax, g_loss, dlogits, static_cast<cudaStream_t>(stream));
 }
 
 int iefvad_profile_read(double* ms, double* work, int64_t* launches) {

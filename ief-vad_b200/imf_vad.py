@@ -188,10 +188,11 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         if not (image_features.is_cuda and event_features.is_cuda):
             raise RuntimeError("IEF-VAD B200 path is CUDA-only: inputs must live on an sm_100a device "
                                "(there is no CPU fallback)")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "the B200 path implements the inference forward only (no autograd, no attention dropout); "
-                "call model.eval() and/or wrap the call in torch.no_grad()")
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                                  or image_features.requires_grad or event_features.requires_grad)
+        if needs_grad or (self.training and self.dropout > 0):
+            # training step (row N3): autograd node over the library's kernels; attention dropout in train() mode
+            return self._forward_train(image_features, event_features)
         if image_features.dim() != 3 or image_features.shape != event_features.shape:
             raise RuntimeError(f"expected two [B, T, {self.embed_dim}] tensors, got {tuple(image_features.shape)} "
                                f"and {tuple(event_features.shape)}")
@@ -241,6 +242,23 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
             out["scores"] = scores
         return out
 
+
+    def _forward_train(self, image_features: torch.Tensor, event_features: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """model/imf_vad.py:109-161 with a grad_fn (train.ForwardFn): what `loss.backward()` of train/ucf_train.py:105 needs.
+        Attention dropout (p = self.dropout) is applied in train() mode only, like nn.MultiheadAttention; every call draws a
+        fresh Philox seed from torch's CPU generator, so `torch.manual_seed` makes runs reproducible."""
+        from . import train
+        if image_features.dim() != 3 or image_features.shape != event_features.shape or image_features.shape[-1] != self.embed_dim:
+            raise RuntimeError(f"expected two [B, T, {self.embed_dim}] tensors, got {tuple(image_features.shape)} "
+                               f"and {tuple(event_features.shape)}")
+        p_drop = float(self.dropout) if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
+        cfg = dict(layers=self.num_layers, steps=self.num_refinement_steps, heads=self.num_heads, p_drop=p_drop, seed=seed,
+                   lambda_ref=float(self.lambda_ref), noise_model=self.noise_model, nu=float(self.nu),
+                   epsilon=float(self.epsilon))
+        outs = train.ForwardFn.apply(cfg, image_features, event_features, *train.param_list(self))
+        keys = ("fused", "logits", "image_mu", "event_mu", "image_logvar", "event_logvar", "w_i", "w_e")
+        return dict(zip(keys, outs))
 
     def _graph_replay(self, device, B, T, D, img, ev, plan, with_scores, launch):
         """One CUDA-graph replay of the forward for a small [B, T] problem, or None (too large, disabled, already

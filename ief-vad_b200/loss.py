@@ -9,7 +9,11 @@ from . import ops
 
 
 def CLAS2(logits: torch.Tensor, labels: torch.Tensor, lengths: torch.Tensor, device=None) -> torch.Tensor:
-    """Same arguments as the reference; `device` is accepted and ignored (the tensors' device is used).
-    Forward value only (this path is inference / forward-only)."""
+    """Same arguments as the reference; `device` is accepted and ignored (the tensors' device is used).  With a
+    `logits` that requires grad the result carries a grad_fn (train.Clas2Fn: the top-k scatter of the BCE gradient),
+    so `loss.backward()` of train/ucf_train.py:105 works."""
+    if torch.is_grad_enabled() and logits.requires_grad:
+        from .train import Clas2Fn
+        return Clas2Fn.apply(logits, labels, lengths)
     loss, _ = ops.clas2(logits, labels, lengths)
     return loss

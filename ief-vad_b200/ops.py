@@ -175,3 +175,115 @@ def auc_ap_multi(scores, pos, member, num_subsets: int, repeat: int = 16):
         _lib.check(_lib.lib.iefvad_auc_ap_multi(s.data_ptr(), p.data_ptr(), m.data_ptr(), s.numel(), repeat,
                                                 num_subsets, out.data_ptr(), None, _stream(s)))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training step (row N3)
+def attention_train_fwd(qkv, B: int, T: int, heads: int, p_drop: float = 0.0, seed: int = 0):
+    """dropout(softmax(q k^T / sqrt(dh))) v of nn.MultiheadAttention in train mode -> (out [B*T, D], lse [B, H, T])."""
+    qkv = _f32c(qkv, "attention_train_fwd")
+    D = qkv.shape[-1] // 3
+    out = torch.empty((B * T, D), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty((B, heads, T), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.lib.iefvad_attention_train_fwd(qkv.data_ptr(), B, T, heads, D // heads, float(p_drop), int(seed),
+                                                       out.data_ptr(), lse.data_ptr(), _stream(qkv)))
+    return out, lse
+
+
+def attention_train_bwd(qkv, out, dout, lse, B: int, T: int, heads: int, p_drop: float = 0.0, seed: int = 0):
+    qkv, out, dout, lse = (_f32c(t, "attention_train_bwd") for t in (qkv, out, dout, lse))
+    D = qkv.shape[-1] // 3
+    dqkv = torch.empty_like(qkv)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.lib.iefvad_attention_train_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, T,
+                                                       heads, D // heads, float(p_drop), int(seed), dqkv.data_ptr(),
+                                                       _stream(qkv)))
+    return dqkv
+
+
+def layernorm_bwd(x, weight, dy, eps: float = 1e-5):
+    """-> (dx, dweight, dbias) of nn.LayerNorm(x) given dy."""
+    x, weight, dy = _f32c(x, "layernorm_bwd"), _f32c(weight, "layernorm_bwd"), _f32c(dy, "layernorm_bwd")
+    D = x.shape[-1]
+    dx = torch.empty_like(x)
+    dw = torch.empty(D, dtype=torch.float32, device=x.device)
+    db = torch.empty(D, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_layernorm_bwd(x.data_ptr(), weight.data_ptr(), dy.data_ptr(), x.numel() // D, D, eps,
+                                                 dx.data_ptr(), dw.data_ptr(), db.data_ptr(), _stream(x)))
+    return dx, dw, db
+
+
+def colsum(a, row_weight=None):
+    """out[c] = sum_r a[r, c] (* row_weight[r]); a [rows, dim]."""
+    a = _f32c(a, "colsum")
+    D = a.shape[-1]
+    rw = _f32c(row_weight, "colsum").reshape(-1) if row_weight is not None else None
+    out = torch.empty(D, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib.iefvad_colsum(a.data_ptr(), _lib.ptr(rw), a.numel() // D, D, out.data_ptr(), _stream(a)))
+    return out
+
+
+def fuse_bwd(mu_i, mu_e, lv_i, lv_e, g_fused=None, g_wi=None, g_we=None, g_mu_i=None, g_mu_e=None, g_lv_i=None,
+             g_lv_e=None, noise_model: str = "StudentT", nu: float = 8, epsilon: float = 1e-8):
+    """Backward of model/imf_vad.py:130-144 -> total gradients (d_mu_i, d_mu_e, d_logvar_i, d_logvar_e)."""
+    factor = 1.0 if noise_model == "Gaussian" else (nu + 1) / nu
+    ins = [_f32c(t, "fuse_bwd") for t in (mu_i, mu_e, lv_i, lv_e)]
+    gs = [(_f32c(t, "fuse_bwd") if t is not None else None) for t in (g_fused, g_wi, g_we, g_mu_i, g_mu_e, g_lv_i, g_lv_e)]
+    outs = [torch.empty_like(ins[0]) for _ in range(4)]
+    with torch.cuda.device(ins[0].device):
+        _lib.check(_lib.lib.iefvad_fuse_bwd(*[t.data_ptr() for t in ins], *[_lib.ptr(t) for t in gs], ins[0].numel(), factor,
+                                            epsilon, *[t.data_ptr() for t in outs], _stream(ins[0])))
+    return tuple(outs)
+
+
+def relu_bwd(dh, h):
+    dh, h = _f32c(dh, "relu_bwd"), _f32c(h, "relu_bwd")
+    out = torch.empty_like(dh)
+    with torch.cuda.device(dh.device):
+        _lib.check(_lib.lib.iefvad_relu_bwd(dh.data_ptr(), h.data_ptr(), dh.numel(), out.data_ptr(), _stream(dh)))
+    return out
+
+
+def axpy_(y, x, alpha: float = 1.0):
+    """y += alpha * x in place (y must be a contiguous fp32 CUDA tensor)."""
+    if y.dtype != torch.float32 or not y.is_contiguous() or not y.is_cuda:
+        raise RuntimeError("axpy_: y must be a contiguous fp32 CUDA tensor")
+    x = _f32c(x, "axpy_")
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib.iefvad_axpy(y.data_ptr(), x.data_ptr(), float(alpha), y.numel(), _stream(y)))
+    return y
+
+
+def outer(a, w):
+    """out[r, c] = a[r] * w[c]."""
+    a, w = _f32c(a, "outer").reshape(-1), _f32c(w, "outer").reshape(-1)
+    out = torch.empty((a.numel(), w.numel()), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib.iefvad_outer(a.data_ptr(), w.data_ptr(), a.numel(), w.numel(), out.data_ptr(), _stream(a)))
+    return out
+
+
+def transpose(x, pad_to: int = 1):
+    """[rows, cols] -> [cols, ld] with ld = rows rounded up to a multiple of pad_to, the tail zero-filled."""
+    x = _f32c(x, "transpose")
+    rows, cols = x.shape
+    ld = (rows + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((cols, ld), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_transpose(x.data_ptr(), rows, cols, out.data_ptr(), ld, _stream(x)))
+    return out
+
+
+def clas2_bwd(logits, means, labels, idx, g_loss=None):
+    x = _f32c(logits, "clas2_bwd")
+    B, T = x.shape[0], x.shape[1]
+    x = x.reshape(B, T).contiguous()
+    labels = _f32c(labels.to(x.device), "clas2_bwd")
+    g = _f32c(g_loss, "clas2_bwd").reshape(1) if g_loss is not None else None
+    out = torch.empty((B, T), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.iefvad_clas2_bwd(x.data_ptr(), means.data_ptr(), labels.data_ptr(), labels.stride(0),
+                                             idx.data_ptr(), B, T, idx.shape[1], _lib.ptr(g), out.data_ptr(), _stream(x)))
+    return out

@@ -293,6 +293,45 @@ int iefvad_event_image(const uint8_t* frames, int64_t B, int C, int H, int W, fl
 int iefvad_bench_gemm(int64_t M, int N, int K, int nsplit, int tile_n, int stages, int epi_kind, int iters,
                       float* ms_per_iter);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step: the pieces `loss.backward()` of train/ucf_train.py:105 needs besides the GEMMs
+ * (which go through iefvad_linear: dgrad = linear(dY, W^T), wgrad = linear(dY^T, X^T)).  All tensors fp32, device.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* nn.MultiheadAttention's core in TRAIN mode (model/imf_vad.py:53,70: dropout 0.1 on the attention weights,
+ * torch/nn/functional.py:6643-6647): out = dropout(softmax(q k^T / sqrt(head_dim))) v per (batch element, head).
+ * qkv [B*T, 3*heads*head_dim] (in-projection output, bias added, q unscaled); out [B*T, heads*head_dim]; lse [B, heads, T]
+ * = log-sum-exp of the scores (saved for the backward).  The dropout mask is a pure function of (seed, head, query, key):
+ * Philox4x32-10 with key = seed and counter = (key >> 2, query, b * heads + h, 0), word (key & 3), dropped when the word
+ * < p_drop * 2^32, kept weights scaled by 1 / (1 - p_drop) - NOT PyTorch's generator stream (no kernel can reproduce that),
+ * so train-mode parity with the reference is statistical; p_drop = 0 gives the eval-mode arithmetic. */
+int iefvad_attention_train_fwd(const float* qkv, int64_t B, int64_t T, int heads, int head_dim, float p_drop, uint64_t seed,
+                               float* out, float* lse, void* stream);
+/* dqkv [B*T, 3*heads*head_dim] <- dout [B*T, heads*head_dim], recomputing the weights (and the same mask) from qkv / lse */
+int iefvad_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int64_t B, int64_t T,
+                               int heads, int head_dim, float p_drop, uint64_t seed, float* dqkv, void* stream);
+/* nn.LayerNorm backward: x [rows, dim] = the layer's input, dy = gradient of its output -> dx, dweight [dim], dbias [dim] */
+int iefvad_layernorm_bwd(const float* x, const float* weight, const float* dy, int64_t rows, int dim, float eps, float* dx,
+                         float* dweight, float* dbias, void* stream);
+/* out[c] = sum_r a[r, c] (bias gradients), optionally weighted by row_weight[r] (classifier weight gradient); fixed order */
+int iefvad_colsum(const float* a, const float* row_weight, int64_t rows, int dim, float* out, void* stream);
+/* Backward of the uncertainty-weighted fusion (model/imf_vad.py:130-144).  g_* = upstream gradients of fused, w_i, w_e and of
+ * the returned image_mu / event_mu / image_logvar / event_logvar (any may be NULL = 0); d_* = total gradients of the four
+ * head outputs (fusion path + their own upstream gradient). */
+int iefvad_fuse_bwd(const float* mu_i, const float* mu_e, const float* logvar_i, const float* logvar_e, const float* g_fused,
+                    const float* g_wi, const float* g_we, const float* g_mu_i, const float* g_mu_e, const float* g_logvar_i,
+                    const float* g_logvar_e, int64_t n, float factor, float epsilon, float* d_mu_i, float* d_mu_e,
+                    float* d_logvar_i, float* d_logvar_e, void* stream);
+int iefvad_relu_bwd(const float* dh, const float* h, int64_t n, float* out, void* stream);      /* out = h > 0 ? dh : 0 */
+int iefvad_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);                /* y += alpha x */
+int iefvad_outer(const float* a, const float* w, int64_t rows, int dim, float* out, void* stream); /* out[r, c] = a[r] w[c] */
+/* dst[c, r] = src[r, c]; dst rows are ld_dst >= rows long, the tail [rows, ld_dst) is zero-filled (GEMM K padding) */
+int iefvad_transpose(const float* src, int64_t rows, int cols, float* dst, int64_t ld_dst, void* stream);
+/* Backward of CLAS2 (train/loss.py:18-30): dlogits [B, T] from the chosen top-k positions idx [B, kmax] (-1 padded) and the
+ * per-row means of iefvad_mil_topk_mean(apply_sigmoid = 1); g_loss: device scalar (NULL = 1). */
+int iefvad_clas2_bwd(const float* logits, const float* means, const float* labels, int64_t label_stride, const int32_t* idx,
+                     int64_t B, int64_t T, int kmax, const float* g_loss, float* dlogits, void* stream);
+
 /* number of CUDA kernels this library has launched since load (process-wide) */
 uint64_t iefvad_launch_count(void);
 /* bumped whenever a library workspace is (re)allocated: a CUDA graph captured around a forward call holds workspace

@@ -336,6 +336,72 @@ def config4_b128_case():
          labels=labels.numpy(), logits=out["logits"].numpy().reshape(128, 256), loss=np.float64(float(loss)))
 
 
+def _reference_train_loss(model, img, ev, lengths, labels, nu):
+    """The loss of train/ucf_train.py:60-102 (classification + cos / norm regulariser + StudentT KL), verbatim."""
+    import math
+    import torch.nn.functional as F
+    outputs = model(img, ev, None, None, lengths)
+    logits = outputs['logits']
+    image_mu, event_mu = outputs['image_mu'], outputs['event_mu']
+    image_logvar, event_logvar = outputs['image_logvar'], outputs['event_logvar']
+    loss_classification = ref_CLAS2(logits, labels, lengths, "cpu")
+    image_mu_norm = F.normalize(image_mu, p=2, dim=-1)
+    event_mu_norm = F.normalize(event_mu, p=2, dim=-1)
+    cos_sim = F.cosine_similarity(image_mu_norm, event_mu_norm, dim=-1)
+    loss_cos = 1 - cos_sim
+    norm_image = torch.norm(image_mu, p=2, dim=-1)
+    norm_event = torch.norm(event_mu, p=2, dim=-1)
+    loss_norm = torch.abs(norm_image - norm_event)
+    loss_reg = loss_cos.mean() + loss_norm.mean()
+    effective_logvar_image = image_logvar + math.log(nu / (nu + 1))
+    effective_logvar_event = event_logvar + math.log(nu / (nu + 1))
+    kl_loss_image = -0.5 * torch.mean(1 + effective_logvar_image - image_mu.pow(2) - effective_logvar_image.exp())
+    kl_loss_event = -0.5 * torch.mean(1 + effective_logvar_event - event_mu.pow(2) - effective_logvar_event.exp())
+    loss_kl = kl_loss_image + kl_loss_event
+    return loss_classification + 1 * loss_reg + 1 * loss_kl, loss_classification
+
+
+def train_step_cases():
+    """Gradients of the reference's training loss (train/ucf_train.py:60-105) by the reference's own autograd, eval mode
+    (attention dropout off - its mask comes from PyTorch's generator, which no other implementation can reproduce).
+    small: every gradient tensor of a 128-d model; full: the 768-d default-seed model on 8 clips of config 4 - gradient
+    norms plus 64 sampled entries per parameter (the full set would be 94 MB)."""
+    with torch.enable_grad():
+        args = synth.default_args(noise_model="StudentT", nu=8, num_refinement_steps=3, visual_head=4)
+        model = synth.build_model(RefMMFMIL, seed=7, embed_dim=128, args=args).eval()
+        synth.perturb_(model, seed=11, scale=0.2)
+        g = torch.Generator("cpu").manual_seed(5)
+        B, T = 3, 40
+        img, ev = torch.randn(B, T, 128, generator=g), torch.randn(B, T, 128, generator=g)
+        lengths = torch.tensor([40, 17, 33])
+        labels = torch.zeros(B, 14)
+        labels[0, 0] = 1.0
+        labels[1, 3] = 1.0
+        labels[2, 5] = 1.0
+        loss, lcls = _reference_train_loss(model, img, ev, lengths, labels, 8)
+        loss.backward()
+        arrays = {"param:" + k: v for k, v in sd_np(model).items()}
+        arrays.update({"grad:" + k: p.grad.numpy().copy() for k, p in model.named_parameters()})
+        arrays.update(img=img.numpy(), ev=ev.numpy(), lengths=lengths.numpy(), labels=labels.numpy(),
+                      loss=np.float64(float(loss)), loss_cls=np.float64(float(lcls)), heads=np.int64(4), nu=np.float64(8))
+        save("train_small.npz", **arrays)
+
+        model = synth.build_model(RefMMFMIL, seed=0).eval()
+        img, ev, lengths, labels = synth.make_c4_batch(8)
+        loss, lcls = _reference_train_loss(model, img, ev, lengths, labels, 8)
+        loss.backward()
+        rng = np.random.default_rng(17)
+        arrays = {"digest": np.array(synth.state_digest(model.state_dict())), "loss": np.float64(float(loss)),
+                  "loss_cls": np.float64(float(lcls)), "lengths": lengths.numpy(), "labels": labels.numpy()}
+        for k, p in model.named_parameters():
+            gnp = p.grad.numpy().reshape(-1)
+            idx = np.sort(rng.choice(gnp.size, size=min(64, gnp.size), replace=False))
+            arrays["idx:" + k] = idx.astype(np.int64)
+            arrays["val:" + k] = gnp[idx].copy()
+            arrays["norm:" + k] = np.float64(np.linalg.norm(gnp.astype(np.float64)))
+        save("train_full.npz", **arrays)
+
+
 def sklearn_cases():
     rng = np.random.default_rng(12)
     arrays = {}
@@ -486,3 +552,5 @@ if __name__ == "__main__":
             config3_case()
         if "config4" in which:
             config4_b128_case()
+        if "train" in which:
+            train_step_cases()
