@@ -72,6 +72,8 @@ _SIGS = {
     "iefvad_outer": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "iefvad_transpose": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
     "iefvad_clas2_bwd": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp]),
+    "iefvad_locmap_proposals": (_i, [_vp, _vp, _vp, _i64, _i, _i] + [_vp] * 5),
+    "iefvad_locmap_match": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i64, C.c_double, _vp, _vp, _vp]),
     "iefvad_bench_gemm": (_i, [_i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "iefvad_launch_count": (C.c_uint64, []),
     "iefvad_alloc_generation": (C.c_uint64, []),

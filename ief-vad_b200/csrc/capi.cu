@@ -13,6 +13,7 @@
 #include "event.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
+#include "locmap.cuh"
 #include "model.cuh"
 #include "rank.cuh"
 #include "shaping.cuh"
@@ -762,6 +763,32 @@ int iefvad_clas2_bwd(const float* logits, const float* means, const float* label
                      int64_t B, int64_t T, int kmax, const float* g_loss, float* dlogits, void* stream) {
   IEF_CHECK(logits && means && labels && idx && dlogits, "iefvad_clas2_bwd: null argument");
   return clas2_bwd(logits, means, labels, label_stride, idx, int(B), int(T), kmax, g_loss, dlogits, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ localisation mAP (N5)
+
+int iefvad_locmap_proposals(const float* pred, const int64_t* vid_off, const int32_t* vid_len, int64_t num_videos,
+                            int num_classes, int max_len, int32_t* prop_count, int32_t* prop_se, float* prop_score,
+                            float* class_score, void* stream) {
+  IEF_CHECK(pred && vid_off && vid_len && prop_count && prop_se && prop_score && class_score, "iefvad_locmap_proposals: null argument");
+  IEF_CHECK(num_videos >= 0 && num_videos < 65536 && num_classes > 0 && num_classes < 65536, "iefvad_locmap_proposals: bad sizes");
+  return locmap_proposals(pred, reinterpret_cast<const long long*>(vid_off), vid_len, int(num_videos), num_classes, max_len,
+                          prop_count, prop_se, prop_score, class_score, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_locmap_match(const int32_t* prop_count, const int32_t* prop_se, const float* prop_score, int64_t num_videos,
+                        int num_classes, const int32_t* gt, const int32_t* gt_off, int64_t num_gt, double iou_threshold,
+                        double* ap, int32_t* n_pred, void* stream) {
+  IEF_CHECK(prop_count && prop_se && prop_score && gt_off && ap && n_pred && (gt || num_gt == 0), "iefvad_locmap_match: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cap = int(num_videos) * 8 > 8192 ? int(num_videos) * 8 : 8192;
+  Scratch sc(st);
+  void *ws, *wi, *wa;
+  IEF_TRY(sc.get(&ws, size_t(num_classes) * cap * 4 * 2));      // rounded up to a power of two inside the kernel
+  IEF_TRY(sc.get(&wi, size_t(num_classes) * cap * 4 * 2));
+  IEF_TRY(sc.get(&wa, size_t(num_gt ? num_gt : 1) * 4));
+  return locmap_match(prop_count, prop_se, prop_score, int(num_videos), num_classes, gt, gt_off, iou_threshold, cap * 2,
+                      static_cast<float*>(ws), static_cast<int*>(wi), static_cast<int*>(wa), ap, n_pred, st);
 }
 
 int iefvad_profile_read(double* ms, double* work, int64_t* launches) {

@@ -156,3 +156,37 @@ def make_event_frames(name: str) -> np.ndarray:
         f1 = np.array([r[1] for r in rows], dtype=np.uint8)
         return np.stack([f0, f1], 0)[None, :, None, :, :].copy()
     raise KeyError(name)
+
+
+def make_locmap_case(n_videos: int = 40, seed: int = 31, num_class: int = 14):
+    """Synthetic inputs of the localisation-mAP row (train/metrics.py:44-136): per-video [T, 14] class predictions with a
+    few raised plateaus (so that thresholding yields proposals), and ground-truth segments that partly overlap them.
+    -> (predictions: list of float32 arrays, gtsegments, gtlabels)."""
+    classlist = ['Normal', 'Abuse', 'Arrest', 'Arson', 'Assault', 'Burglary', 'Explosion', 'Fighting', 'RoadAccidents',
+                 'Robbery', 'Shooting', 'Shoplifting', 'Stealing', 'Vandalism']
+    rng = np.random.default_rng(seed)
+    preds, segs, labels = [], [], []
+    for v in range(n_videos):
+        T = int(rng.integers(20, 400))
+        p = (0.05 * rng.standard_normal((T, num_class)) + 0.1).astype(np.float32)
+        p[:, rng.integers(0, num_class, 2)] -= 0.5                        # a couple of classes with a non-positive score
+        vs, vl = [], []
+        for _ in range(int(rng.integers(1, 4))):
+            c = int(rng.integers(0, num_class))
+            a = int(rng.integers(0, T - 8))
+            b = min(T, a + int(rng.integers(4, max(5, T // 3))))
+            p[a:b, c] += np.float32(rng.uniform(0.3, 0.9))
+            shift = int(rng.integers(-6, 7))
+            vs.append([max(0, a + shift), max(1, b + shift)])
+            vl.append(classlist[c])
+        preds.append(p)
+        segs.append(vs)
+        labels.append(vl)
+    for c, name in enumerate(classlist):                                  # every class gets at least one proposal + one gt
+        v = c % n_videos
+        T = preds[v].shape[0]
+        preds[v][2:9, c] += np.float32(1.5)
+        preds[v][:, c] += np.float32(0.6)
+        segs[v].append([1, 10])
+        labels[v].append(name)
+    return preds, segs, labels

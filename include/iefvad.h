@@ -332,6 +332,28 @@ int iefvad_transpose(const float* src, int64_t rows, int cols, float* dst, int64
 int iefvad_clas2_bwd(const float* logits, const float* means, const float* labels, int64_t label_stride, const int32_t* idx,
                      int64_t B, int64_t T, int kmax, const float* g_loss, float* dlogits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Temporal-localisation mAP - replaces getDetectionMAP / getLocMAP / nms, train/metrics.py:19-136
+ * (imported by train/ucf_test.py:13 as dmAP, never called by the reference).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per (video, class): class score = mean of the top int(T/16) values of the column (:60-64); for classes with a positive
+ * score, runs of >= 2 frames above max - 0.6 (max - min) become proposals scored max + 0.7 class score (:75-83), sorted by
+ * score, greedy NMS at IoU 0.6 (:19-41).  pred: the videos' [T_v, num_classes] fp32 predictions back to back (video v at
+ * row vid_off[v], vid_len[v] <= 4096 rows); prop_count [V, C] (-1: more than 512 proposals, unsupported), prop_se
+ * [V, C, 512, 2] (start, end), prop_score [V, C, 512], class_score [V, C]. */
+int iefvad_locmap_proposals(const float* pred, const int64_t* vid_off, const int32_t* vid_len, int64_t num_videos,
+                            int num_classes, int max_len, int32_t* prop_count, int32_t* prop_se, float* prop_score,
+                            float* class_score, void* stream);
+/* Per class: proposals of all videos sorted by score (:96), greedy matching against that class's ground-truth segments with
+ * deletion of the matched one (:104-122, IoU of the integer frame sets >= iou_threshold), ap[c] = sum(precision * tp) / #gt
+ * (:123-128; 0 without a true positive).  gt [num_gt, 3] = (video, start, end) GROUPED BY CLASS in the reference's order,
+ * class c owning rows [gt_off[c], gt_off[c + 1]); n_pred[c] = proposals of class c (the reference returns 0 for the whole
+ * call as soon as one class has none, :92-93 - the host side reproduces that). */
+int iefvad_locmap_match(const int32_t* prop_count, const int32_t* prop_se, const float* prop_score, int64_t num_videos,
+                        int num_classes, const int32_t* gt, const int32_t* gt_off, int64_t num_gt, double iou_threshold,
+                        double* ap, int32_t* n_pred, void* stream);
+
 /* number of CUDA kernels this library has launched since load (process-wide) */
 uint64_t iefvad_launch_count(void);
 /* bumped whenever a library workspace is (re)allocated: a CUDA graph captured around a forward call holds workspace

@@ -511,6 +511,98 @@ def event_images(frames: np.ndarray, threshold=25, clamp=10) -> np.ndarray:
 # --------------------------------------------------------------------------
 
 
+# --------------------------------------------------------------------------
+# N5: temporal-localisation mAP (train/metrics.py:19-136; never called by the reference's live loops)
+# --------------------------------------------------------------------------
+LOC_CLASSLIST = ['Normal', 'Abuse', 'Arrest', 'Arson', 'Assault', 'Burglary', 'Explosion', 'Fighting', 'RoadAccidents',
+                 'Robbery', 'Shooting', 'Shoplifting', 'Stealing', 'Vandalism']          # train/metrics.py:53
+
+
+def loc_nms(dets: np.ndarray, thresh: float = 0.6) -> List[int]:
+    """train/metrics.py:19-41: greedy 1-D NMS over [start, end] rows already sorted by score -> kept indices."""
+    if len(dets) == 0:
+        return []
+    dets = np.asarray(dets, dtype=np.float64)
+    x1, x2 = dets[:, 0], dets[:, 1]
+    lengths = x2 - x1
+    order = np.arange(len(dets))
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(int(i))
+        xx1 = np.maximum(x1[i], x1[order[1:]])
+        xx2 = np.minimum(x2[i], x2[order[1:]])
+        inter = np.maximum(0.0, xx2 - xx1)
+        ovr = inter / (lengths[i] + lengths[order[1:]] - inter)
+        order = order[np.where(ovr <= thresh)[0] + 1]
+    return keep
+
+
+def loc_map(predictions, th: float, gtsegments, gtlabels, exclude_normal: bool = False):
+    """train/metrics.py:44-126 (`getLocMAP`), statement by statement; predictions[i] is a float32 [T_i, 14] array."""
+    if exclude_normal is True:                                               # :45-48
+        predictions = predictions[:140]
+    c_score, mod = [], []
+    for p in predictions:                                                    # :58-65
+        p = np.asarray(p, dtype=np.float32)
+        pp = -np.sort(-p, axis=0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                c_s = np.mean(pp[:int(p.shape[0] / 16), :], axis=0)
+        c_score.append(c_s)
+        mod.append(p * (c_s > 0.0))
+    ap = []
+    for c in range(14):                                                      # :68
+        segment_predict = []
+        for i in range(len(mod)):                                            # :71-88
+            tmp = mod[i][:, c]
+            if tmp.size == 0:
+                continue
+            threshold = np.max(tmp) - (np.max(tmp) - np.min(tmp)) * np.float64(0.6)
+            vid_pred = np.concatenate([np.zeros(1), (tmp > threshold).astype('float32'), np.zeros(1)], axis=0)
+            diff = vid_pred[1:] - vid_pred[:-1]
+            s = np.nonzero(diff == 1)[0]
+            e = np.nonzero(diff == -1)[0]
+            cand = []
+            for j in range(len(s)):
+                if e[j] - s[j] >= 2:
+                    cand.append([i, s[j], e[j], np.max(tmp[s[j]:e[j]]) + np.float32(0.7) * c_score[i][c]])
+            if cand:
+                cand = np.array(cand)
+                cand = cand[np.argsort(-cand[:, -1], kind="stable")]
+                segment_predict.extend(list(cand[loc_nms(cand[:, 1:-1], 0.6)]))
+        segment_predict = np.array(segment_predict)
+        if len(segment_predict) == 0:                                        # :92-93
+            return 0
+        segment_predict = segment_predict[np.argsort(-segment_predict[:, 3], kind="stable")]       # :96
+        segment_gt = [[i, gtsegments[i][j][0], gtsegments[i][j][1]] for i in range(len(gtsegments))
+                      for j in range(len(gtsegments[i])) if gtlabels[i][j] == LOC_CLASSLIST[c]]       # :99-100
+        gtpos = len(segment_gt)
+        tp, fp = [], []
+        for i in range(len(segment_predict)):                                # :104-122
+            flag, best_iou, best_j = 0.0, 0.0, -1
+            for j in range(len(segment_gt)):
+                if segment_predict[i][0] == segment_gt[j][0]:
+                    gs, ge = int(segment_gt[j][1]), int(segment_gt[j][2])
+                    ps, pe = int(segment_predict[i][1]), int(segment_predict[i][2])
+                    lg, lp = max(ge - gs, 0), max(pe - ps, 0)
+                    inter = max(min(pe, ge) - max(ps, gs), 0) if lg and lp else 0
+                    iou = float(inter) / float(lg + lp - inter)
+                    if iou >= th:
+                        flag = 1.0
+                        if iou > best_iou:
+                            best_iou, best_j = iou, j
+            if flag > 0:
+                del segment_gt[best_j]
+            tp.append(flag)
+            fp.append(1.0 - flag)
+        tp_c, fp_c = np.cumsum(tp), np.cumsum(fp)
+        ap.append(0.0 if sum(tp) == 0 else float(np.sum((tp_c / (fp_c + tp_c)) * tp) / gtpos))    # :123-127
+    return 100 * np.mean(ap)
+
+
 def max_norm_err(x: np.ndarray, ref: np.ndarray) -> float:
     """max|x - ref| / max|ref| per tensor."""
     ref = np.asarray(ref, dtype=np.float64)

@@ -402,6 +402,19 @@ def train_step_cases():
         save("train_full.npz", **arrays)
 
 
+def locmap_case():
+    """train/metrics.py run as-is: getDetectionMAP on synthetic class predictions (synth.make_locmap_case)."""
+    from train import metrics as ref_metrics
+    import warnings
+    preds, segs, labels = synth.make_locmap_case()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dmap, ious = ref_metrics.getDetectionMAP([p.copy() for p in preds], segs, labels, excludeNormal=False)
+        short = ref_metrics.getLocMAP([p.copy() for p in preds[:9]], 0.3, segs[:9], labels[:9], False)     # a class without proposals -> 0
+    print("locmap:", dmap, ious, "first 9 videos:", short)
+    save("locmap.npz", dmap=np.array(dmap, dtype=np.float64), ious=np.array(ious), short=np.float64(short))
+
+
 def sklearn_cases():
     rng = np.random.default_rng(12)
     arrays = {}
@@ -554,3 +567,5 @@ if __name__ == "__main__":
             config4_b128_case()
         if "train" in which:
             train_step_cases()
+        if "locmap" in which:
+            locmap_case()

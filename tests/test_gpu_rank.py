@@ -224,3 +224,22 @@ def test_evaluator_matches_reference_eval_loop(ops):
     rep = np.repeat(np.concatenate([np.concatenate(by[c]) for c in ab]).astype(np.float64), 16)
     # Ano-AUC concatenates class by class (train/ucf_test.py:339-345); AUC is order independent
     assert abs(res["ano_AUC"] - O.roc_auc_score(np.concatenate([np.concatenate(gby[c]) for c in ab]), rep)) < 1e-12
+
+
+def test_localisation_map_matches_reference_and_oracle():
+    """Row N5: getDetectionMAP on the GPU (csrc/locmap.cu) against the reference's own output (train/metrics.py run as-is,
+    tests/golden/locmap.npz) and against the oracle on further cases incl. the `return 0` quirk."""
+    from iefvad_b200 import metrics, synth
+    z = load_golden("locmap.npz")
+    preds, segs, labels = synth.make_locmap_case()
+    dmap, ious = metrics.getDetectionMAP([torch.from_numpy(p).cuda() for p in preds], segs, labels)
+    assert ious == [0.1, 0.2, 0.3, 0.4, 0.5]
+    assert np.max(np.abs(np.array(dmap) - z["dmap"])) < 1e-6, (dmap, z["dmap"])
+    assert abs(metrics.getLocMAP(preds[:9], 0.3, segs[:9], labels[:9], False) - float(z["short"])) < 1e-6
+    dead = [p.copy() for p in preds]
+    for p in dead:
+        p[:, 5] = -1.0
+    assert metrics.getLocMAP(dead, 0.3, segs, labels, False) == 0
+    p2, s2, l2 = synth.make_locmap_case(n_videos=120, seed=77)
+    for th in (0.1, 0.5):
+        assert abs(metrics.getLocMAP(p2, th, s2, l2, False) - O.loc_map(p2, th, s2, l2)) < 1e-6

@@ -152,3 +152,17 @@ def test_event_synthesis_restatement_matches_reference(name):
         assert ev.shape == (frames.shape[0], 3) + frames.shape[2:4]
         for c in range(3):
             assert np.array_equal(ev[:, c], z[f"{name}:{thr}:{clamp}:event"], equal_nan=True)
+
+
+def test_localisation_map_oracle_matches_reference_metrics():
+    """Row N5: oracle.loc_map (restating train/metrics.py:44-126) against the reference's own getDetectionMAP output."""
+    from iefvad_b200 import synth
+    z = load_golden("locmap.npz")
+    preds, segs, labels = synth.make_locmap_case()
+    for th, want in zip(z["ious"], z["dmap"]):
+        assert abs(O.loc_map(preds, float(th), segs, labels) - float(want)) < 1e-9
+    assert abs(O.loc_map(preds[:9], 0.3, segs[:9], labels[:9]) - float(z["short"])) < 1e-9
+    dead = [p.copy() for p in preds]
+    for p in dead:
+        p[:, 5] = -1.0                                  # no proposal for class 5 anywhere -> the reference returns 0 (:92-93)
+    assert O.loc_map(dead, 0.3, segs, labels) == 0
