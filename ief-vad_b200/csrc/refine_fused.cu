@@ -46,7 +46,7 @@ constexpr int NCH1 = D / 256;                  // 3 h chunks of 256 hidden units
 constexpr int NCH2 = D / 128;                  // 6 x chunks of 128 columns
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
-constexpr int STAGES = 4;
+constexpr int STAGES = 5;
 constexpr uint32_t kABox = BM * BK * 2;        // 16 KB: 128 rows x 64 k of fp16(x)
 constexpr uint32_t kW1Box = 128 * BK * 2;      // 16 KB: this CTA's 128 of the 256 W1 rows x 64 k
 constexpr uint32_t kW2Box = 64 * BK * 2;       //  8 KB: this CTA's 64 of the 128 W2 rows x 64 k (4 per stage)
@@ -55,7 +55,7 @@ constexpr uint32_t kStage = kABox + kW1Box;    // 32 KB
 // which the warp's share of x moves between "one thread = one row" (the TMEM view) and "one instruction = four whole
 // 128-byte rows" (the only global access pattern the LSU serves at full rate)
 constexpr uint32_t kOffStageBuf = STAGES * kStage;
-constexpr uint32_t kWarpStage = 12288;     // Hb, Lb: the (hi, lo) chunk coming in; Ob: results going out
+constexpr uint32_t kWarpStage = 8192;      // Hb, Lb: the (hi, lo) chunk coming in, then the new pair going out
 constexpr uint32_t kOffBar = kOffStageBuf + kEpiWarps * kWarpStage;
 constexpr uint32_t kSmemBytes = 1024 + kOffBar + 256;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -315,7 +315,7 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t tlane = tmem_base + (uint32_t(q * 32) << 16);
     const float nlam = -p.lambda;
     const uint32_t Hb = smem_u32(smem + kOffStageBuf + size_t(warp - 2) * kWarpStage);      // shared-space addresses
-    const uint32_t Lb = Hb + 4096, Ob = Hb + 8192;
+    const uint32_t Lb = Hb + 4096;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp == 2;
     long long w_acc = 0, w_a2f = 0;
     const long long t_begin = clock64();
@@ -429,8 +429,6 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           h4[c] = lds128(Hb + sw128(lane, c));
           l4[c] = lds128(Lb + sw128(lane, c));
         }
-        __syncwarp();                            // every lane holds its row: Hb / Lb may take the next chunk
-        if (n + 1 < NCH2) fetch(n + 1);          // in flight while this chunk is computed and written out
         const float4* bp = reinterpret_cast<const float4*>(b2 + col0);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -459,27 +457,35 @@ refine_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             l4[g] = make_uint4(nl[0], nl[1], nl[2], nl[3]);
           }
         }
-        // out through Ob, one 4 KB tile at a time: my row in (swizzled like a TMA box), one bulk tensor store out
+        // out through the tiles the chunk came in (every lane rewrites exactly the slots it read): two bulk tensor stores;
+        // the next chunk's copies start as soon as the stores have read the tiles
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (lane == 0) bulk_wait_read<0>();    // the previous store has finished reading Ob
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 w;
-            if (!last) w = half ? l4[c] : h4[c];
-            else w = make_uint4(__float_as_uint(v[32 * half + 4 * c]), __float_as_uint(v[32 * half + 4 * c + 1]),
-                                __float_as_uint(v[32 * half + 4 * c + 2]), __float_as_uint(v[32 * half + 4 * c + 3]));
-            sts128(Ob + sw128(lane, c), w);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (!last) tma_store_2d_s(half ? &tmSL : &tmSH, Ob, col0, int(wrow0));
-            else tma_store_2d_s(&tmSO, Ob, col0 + 32 * half, int(wrow0));
-            bulk_commit();
+        for (int c = 0; c < 8; ++c) {
+          if (!last) {
+            sts128(Hb + sw128(lane, c), h4[c]);
+            sts128(Lb + sw128(lane, c), l4[c]);
+          } else {                                // fp32 result: columns [0, 32) of this warp's 64 in Hb, [32, 64) in Lb
+            sts128(Hb + sw128(lane, c), make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                                                   __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+            sts128(Lb + sw128(lane, c), make_uint4(__float_as_uint(v[32 + 4 * c]), __float_as_uint(v[32 + 4 * c + 1]),
+                                                   __float_as_uint(v[32 + 4 * c + 2]), __float_as_uint(v[32 + 4 * c + 3])));
           }
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (!last) {
+            tma_store_2d_s(&tmSH, Hb, col0, int(wrow0));
+            tma_store_2d_s(&tmSL, Lb, col0, int(wrow0));
+          } else {
+            tma_store_2d_s(&tmSO, Hb, col0, int(wrow0));
+            tma_store_2d_s(&tmSO, Lb, col0 + 32, int(wrow0));
+          }
+          bulk_commit();
+          bulk_wait_read<0>();                    // the stores have read Hb / Lb
+        }
+        __syncwarp();
+        if (n + 1 < NCH2) fetch(n + 1);
       }
       // Published after the next unit's first accumulator read-out (waiting for the stores here would delay it) - but only
       // when that next unit cannot depend on this one: with more tiles than pairs its predecessor (s, t') lies before this

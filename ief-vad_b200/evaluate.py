@@ -231,6 +231,9 @@ class Evaluator:
 
     def finish(self, host_table: torch.Tensor) -> Dict[str, object]:
         """Wait for the stream and unpack a metrics table returned by `metrics_async`."""
+        side = self.__dict__.get("_side_stream")
+        if side is not None:
+            side.synchronize()
         torch.cuda.current_stream(self.device).synchronize()
         if not self.model.temporal.check_finite():          # range guard of the 16-bit plans (fp16 saturates at 65 504)
             self.model.temporal._raise_overflow()
@@ -248,7 +251,7 @@ class Evaluator:
         return self.finish(self.metrics_async(scores))
 
     def step(self, host_inputs: bool = False, with_metrics: bool = True, sync: bool = True,
-             extras: Sequence[str] = ()) -> Dict[str, object]:
+             extras: Sequence[str] = (), overlap: bool = False) -> Dict[str, object]:
         """One evaluation pass.  With sync=False nothing waits for the device: the returned dict holds the device
         score vector and, under "pending", the pinned metrics table to hand to `finish()` later.
 
@@ -257,7 +260,13 @@ class Evaluator:
         of every frame, reduced inside the fusion kernel) and "classwise_wi" / "classwise_we" (class key -> the frames of
         that class's videos, list order); "wide" adds this rank's compact [my rows, D] "fused", "image_mu", "event_mu"
         (rows of `self.mine` videos back to back) and "classwise_fused" / "classwise_image_mu" / "classwise_event_mu" for
-        the classes of this rank's videos."""
+        the classes of this rank's videos.
+
+        overlap (with sync=False): the collective and the ranking of this pass run on a side stream, so in a loop of passes
+        they hide behind the NEXT pass's forward (they are a handful of latency-bound launches that would otherwise sit
+        between two forwards on every rank); `finish()` waits for the side stream."""
+        if overlap and not sync and with_metrics and not extras:
+            return self._step_overlapped(host_inputs)
         extra: Dict[str, torch.Tensor] = {}
         unknown = set(extras) - {"w_mean", "wide"}
         if unknown:
@@ -298,6 +307,18 @@ class Evaluator:
                 res[k] = extra[k]
                 res["classwise_" + k] = {name: extra[k][idx] for name, idx in local.items()}
         return res
+
+    def _step_overlapped(self, host_inputs: bool) -> Dict[str, object]:
+        main = torch.cuda.current_stream(self.device)
+        side = self.__dict__.setdefault("_side_stream", None) or torch.cuda.Stream(self.device)
+        self._side_stream = side
+        packed = self.local_scores(host_inputs)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            packed.record_stream(side)
+            scores = self.gather(packed)
+            pending = self.metrics_async(scores)
+        return {"pending": pending, "scores": scores}
 
     def _class_rows(self, local: bool = False) -> Dict[str, torch.Tensor]:
         """class key -> device index vector of that class's frames: into the list-order vectors, or (local=True) into this
