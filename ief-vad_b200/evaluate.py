@@ -338,8 +338,9 @@ class Evaluator:
 
     def step_breakdown(self, reps: int = 5, host_inputs: bool = False) -> Dict[str, float]:
         """Where a step's device time goes: forward over my chunks | the single collective (+ re-ordering into list
-        order) | ranking (AUC / AP of every subset).  CUDA events on the launching stream, mean of `reps` steps.  At
-        world > 1 the collective's time includes waiting for the slowest rank's forward."""
+        order) | ranking (AUC / AP of every subset).  CUDA events on the launching stream, MEDIAN of `reps` steps (a host
+        hiccup between two launches shows up as idle stream time in that step's events).  At world > 1 the collective's
+        time includes waiting for the slowest rank's forward."""
         marks = []
         for _ in range(reps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -353,7 +354,8 @@ class Evaluator:
             marks.append(ev)
         torch.cuda.current_stream(self.device).synchronize()
         names = ("forward_ms", "collective_ms", "ranking_ms")
-        return {nm: round(sum(ev[i].elapsed_time(ev[i + 1]) for ev in marks) / reps, 4) for i, nm in enumerate(names)}
+        med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
+        return {nm: round(med([ev[i].elapsed_time(ev[i + 1]) for ev in marks]), 4) for i, nm in enumerate(names)}
 
     # bytes moved by a host-input step (for bench.py's e2e block)
     def h2d_bytes(self) -> int:
