@@ -68,6 +68,7 @@ _SIGS = {
     "iefvad_colsum": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "iefvad_fuse_bwd": (_i, [_vp] * 11 + [_i64, _f, _f] + [_vp] * 5),
     "iefvad_relu_bwd": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "iefvad_quickgelu": (_i, [_vp, _i64, _vp, _vp]),
     "iefvad_axpy": (_i, [_vp, _vp, _f, _i64, _vp]),
     "iefvad_outer": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "iefvad_transpose": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),

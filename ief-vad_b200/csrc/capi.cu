@@ -391,7 +391,7 @@ int iefvad_linear(const float* x, const float* w, const float* bias, const float
                   int64_t rows, int in_f, int out_f, int plan, int tile_n, float* out, void* stream) {
   IEF_CHECK(x && w && out, "iefvad_linear: null argument");
   IEF_CHECK(rows >= 0 && rows < (1LL << 31), "iefvad_linear: bad row count");
-  IEF_CHECK(plan >= -1 && plan <= 1, "iefvad_linear: plan must be -1 (fp32), 0 (bf16) or 1 (split-bf16)");
+  IEF_CHECK(plan >= -1 && plan <= 2, "iefvad_linear: plan must be -1 (fp32), 0 (bf16), 1 (split-bf16) or 2 (fp16)");
   if (rows == 0) return IEFVAD_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int sms = 0;
@@ -407,11 +407,17 @@ int iefvad_linear(const float* x, const float* w, const float* bias, const float
   IEF_TRY(sc.get(&xl, size_t(rows) * in_f * 2));
   IEF_TRY(sc.get(&wh, size_t(out_f) * in_f * 2));
   IEF_TRY(sc.get(&wl, size_t(out_f) * in_f * 2));
-  IEF_TRY(ingest(x, IEFVAD_DT_F32, rows * in_f, nullptr, (bf16*)xh, (bf16*)xl, sms, st));
-  IEF_TRY(ingest(w, IEFVAD_DT_F32, int64_t(out_f) * in_f, nullptr, (bf16*)wh, (bf16*)wl, sms, st));
+  if (plan == 2) {                  // fp16 (E5M10) operands, one MMA pass: what the default plan HH runs everywhere
+    IEF_TRY(to_half(x, rows * in_f, xh, sms, st));
+    IEF_TRY(to_half(w, int64_t(out_f) * in_f, wh, sms, st));
+  } else {
+    IEF_TRY(ingest(x, IEFVAD_DT_F32, rows * in_f, nullptr, (bf16*)xh, (bf16*)xl, sms, st));
+    IEF_TRY(ingest(w, IEFVAD_DT_F32, int64_t(out_f) * in_f, nullptr, (bf16*)wh, (bf16*)wl, sms, st));
+  }
   GemmTcArgs g;
   g.A_hi = (bf16*)xh; g.A_lo = (bf16*)xl; g.W_hi = (bf16*)wh; g.W_lo = (bf16*)wl;
   g.M = int(rows); g.N = out_f; g.K = in_f; g.lda = in_f; g.ldw = in_f; g.nsplit = plan == 1 ? 3 : 1;
+  g.fp16 = plan == 2 ? 1 : 0;
   g.force_bn = tile_n == 512 ? 256 : tile_n;          // 512 = 256-column tiles on CTA pairs
   g.force_cg = tile_n == 512 ? 2 : (tile_n ? 1 : 0);
   return gemm_tc(g, ep, sms, st);
@@ -738,6 +744,13 @@ int iefvad_relu_bwd(const float* dh, const float* h, int64_t n, float* out, void
   int sms = 0;
   IEF_TRY(current_sms(&sms));
   return relu_bwd(dh, h, n, out, sms, static_cast<cudaStream_t>(stream));
+}
+
+int iefvad_quickgelu(const float* x, int64_t n, float* out, void* stream) {
+  IEF_CHECK(x && out, "iefvad_quickgelu: null argument");
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  return quickgelu(x, n, out, sms, static_cast<cudaStream_t>(stream));
 }
 
 int iefvad_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {

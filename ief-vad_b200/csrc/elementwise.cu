@@ -311,10 +311,17 @@ pack_chunks_kernel(const uint4* __restrict__ src, const ChunkItem* __restrict__ 
 }
 
 __global__ void __launch_bounds__(kThreads)
-inverse_rowmap_items_kernel(const ChunkItem* __restrict__ items, const ChunkAux* __restrict__ aux, int* __restrict__ inv) {
+inverse_rowmap_items_kernel(const ChunkItem* __restrict__ items, const ChunkAux* __restrict__ aux, int* __restrict__ inv,
+                            const int* __restrict__ rowmap, long long row_base, int* __restrict__ status) {
   const ChunkItem it = items[blockIdx.x];
   const ChunkAux ax = aux[blockIdx.x];
-  for (int t = threadIdx.x; t < ax.span; t += blockDim.x) inv[it.start + t] = t < it.valid ? ax.out + t : -1;
+  bool bad = false;
+  for (int t = threadIdx.x; t < ax.span; t += blockDim.x) {
+    inv[it.start + t] = t < it.valid ? ax.out + t : -1;
+    // pad de-duplication takes the valid rows of a chunk to be its FIRST rows: the caller's row map must say the same
+    if (rowmap && t < it.valid && (long long)rowmap[ax.out + t] - row_base != ax.src + t) bad = true;
+  }
+  if (bad && status) atomicOr(status, 2);
 }
 
 // one warp per output row: 16-byte vectors, D % 8 == 0
@@ -497,9 +504,10 @@ int pack_chunks(const void* src16, const ChunkItem* items, const ChunkAux* aux, 
   return IEFVAD_OK;
 }
 
-int inverse_rowmap_items(const ChunkItem* items, const ChunkAux* aux, int n_items, int* inv, cudaStream_t stream) {
+int inverse_rowmap_items(const ChunkItem* items, const ChunkAux* aux, int n_items, int* inv, cudaStream_t stream,
+                         const int* rowmap, long long row_base, int* status) {
   if (n_items == 0) return IEFVAD_OK;
-  inverse_rowmap_items_kernel<<<n_items, kThreads, 0, stream>>>(items, aux, inv);
+  inverse_rowmap_items_kernel<<<n_items, kThreads, 0, stream>>>(items, aux, inv, rowmap, row_base, status);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

@@ -29,8 +29,11 @@ struct ChunkAux { long long src; int span; int out; };          // src = first s
 // dst[start + t] = src16[src + t] (t < valid), 0 elsewhere in the span; 16-bit rows of D elements
 int pack_chunks(const void* src16, const ChunkItem* items, const ChunkAux* aux, int n_items, int D, void* dst16,
                 cudaStream_t stream);
-// inv[start + t] = out + t (t < valid), -1 elsewhere in the span
-int inverse_rowmap_items(const ChunkItem* items, const ChunkAux* aux, int n_items, int* inv, cudaStream_t stream);
+// inv[start + t] = out + t (t < valid), -1 elsewhere in the span.  rowmap (optional, dense sources): the caller's compact
+// row map, checked to be the prefix map the packed layout assumes (rowmap[out + t] - row_base == src + t); bit 1 of
+// *status is set otherwise
+int inverse_rowmap_items(const ChunkItem* items, const ChunkAux* aux, int n_items, int* inv, cudaStream_t stream,
+                         const int* rowmap = nullptr, long long row_base = 0, int* status = nullptr);
 
 // inv[rowmap[j] - row_base] = j for j < n_rows, every other entry of inv[0, M) = -1
 int inverse_rowmap(const int* rowmap, long long row_base, long long n_rows, long long M, int* inv, int num_sms,

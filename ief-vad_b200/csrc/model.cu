@@ -362,7 +362,8 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     if (dedup && n_items == 0) continue;                 // no valid row in this slab
     if (direct_compact) {
       IEF_TRY(inv_map.reserve(size_t(Me) * sizeof(int)));
-      if (dedup) IEF_TRY(inverse_rowmap_items(items_dev.as<ChunkItem>(), aux_dev.as<ChunkAux>(), n_items, inv_map.as<int>(), stream));
+      if (dedup) IEF_TRY(inverse_rowmap_items(items_dev.as<ChunkItem>(), aux_dev.as<ChunkAux>(), n_items, inv_map.as<int>(), stream,
+                                              (vr->chunk_start && vr->chunk_valid) ? nullptr : vr->rowmap + out0, vr->row_base + row0, status.as<int>()));
       else IEF_TRY(inverse_rowmap(vr->rowmap + out0, vr->row_base + row0, Mo, M, inv_map.as<int>(), num_sms, stream));
     }
     // q / k rows: d_h padded to a multiple of 64 for the 128-byte-swizzled kernels; the short-sequence kernel takes

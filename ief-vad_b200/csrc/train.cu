@@ -398,6 +398,14 @@ relu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h, long 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = h[i] > 0.f ? dh[i] : 0.f;
 }
+// QuickGELU of model/module.py:15-17: x * sigmoid(1.702 x)
+__global__ void __launch_bounds__(kThreads)
+quickgelu_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = v / (1.f + expf(-1.702f * v));
+  }
+}
 __global__ void __launch_bounds__(kThreads)
 axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -555,6 +563,14 @@ int fuse_bwd(const float* mu_i, const float* mu_e, const float* lv_i, const floa
 int relu_bwd(const float* dh, const float* h, long long n, float* out, int num_sms, cudaStream_t stream) {
   if (n == 0) return IEFVAD_OK;
   relu_bwd_kernel<<<grid_for(n, num_sms), kThreads, 0, stream>>>(dh, h, n, out);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int quickgelu(const float* x, long long n, float* out, int num_sms, cudaStream_t stream) {
+  if (n == 0) return IEFVAD_OK;
+  quickgelu_kernel<<<grid_for(n, num_sms), kThreads, 0, stream>>>(x, n, out);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

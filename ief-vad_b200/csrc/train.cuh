@@ -23,6 +23,7 @@ int fuse_bwd(const float* mu_i, const float* mu_e, const float* lv_i, const floa
              const float* g_we, const float* g_mu_i, const float* g_mu_e, const float* g_lv_i, const float* g_lv_e, long long n,
              float factor, float eps, float* d_mu_i, float* d_mu_e, float* d_lv_i, float* d_lv_e, int num_sms, cudaStream_t stream);
 int relu_bwd(const float* dh, const float* h, long long n, float* out, int num_sms, cudaStream_t stream);
+int quickgelu(const float* x, long long n, float* out, int num_sms, cudaStream_t stream);
 int axpy(float* y, const float* x, float alpha, long long n, int num_sms, cudaStream_t stream);
 int outer(const float* a, const float* w, long long rows, int D, float* out, int num_sms, cudaStream_t stream);
 int transpose_f32(const float* src, long long rows, int cols, float* dst, long long ld_dst, cudaStream_t stream);

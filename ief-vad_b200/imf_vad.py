@@ -128,6 +128,9 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         with torch.cuda.device(self._handle_device):
             _lib.check(_lib.lib.iefvad_model_check_finite(self._handle, C.byref(flag),
                                                           torch.cuda.current_stream(self._handle_device).cuda_stream))
+        if flag.value & 2:
+            raise RuntimeError("pad de-duplication needs the valid rows of every chunk to be its FIRST rows: the row map passed "
+                               "to scores() is not the prefix map; set model.temporal.pad_dedup = False for other maps")
         return flag.value == 0
 
     def _raise_overflow(self):

@@ -15,11 +15,24 @@ from .ops import PLAN_CODES, _f32c, _stream
 
 
 class LayerNorm(nn.LayerNorm):
-    """module.py:7-12 (fp32 upcast); parameters only - the arithmetic happens in the fused call."""
+    """module.py:7-12: LayerNorm computed in fp32 whatever the input dtype.  Inside `Transformer` the arithmetic happens
+    in the fused call; called on its own it runs the library's LayerNorm kernel."""
+
+    def forward(self, x: torch.Tensor):
+        from . import ops
+        if tuple(self.normalized_shape) != (x.shape[-1],):
+            raise RuntimeError("LayerNorm over the last dimension only")
+        out = ops.layernorm(x, self.weight, self.bias, eps=self.eps)           # upcasts to fp32 (:9-11)
+        return out.to(x.dtype)
 
 
 class QuickGELU(nn.Module):
-    """module.py:15-17: x * sigmoid(1.702 x), applied in the c_fc GEMM epilogue."""
+    """module.py:15-17: x * sigmoid(1.702 x).  Inside `Transformer` it is the c_fc GEMM's epilogue; called on its own it
+    runs the library's element-wise kernel."""
+
+    def forward(self, x: torch.Tensor):
+        from . import ops
+        return ops.quickgelu(x)
 
 
 class ResidualAttentionBlock(nn.Module):

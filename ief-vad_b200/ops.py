@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-PLAN_CODES = {"fp32": -1, "bf16": 0, "split": 1}
+PLAN_CODES = {"fp32": -1, "bf16": 0, "split": 1, "fp16": 2}      # fp16: iefvad_linear only (the HH plan's GEMM)
 ACTS = {None: 0, "none": 0, "relu": 1, "quickgelu": 2}
 
 
@@ -236,6 +236,15 @@ def fuse_bwd(mu_i, mu_e, lv_i, lv_e, g_fused=None, g_wi=None, g_we=None, g_mu_i=
         _lib.check(_lib.lib.iefvad_fuse_bwd(*[t.data_ptr() for t in ins], *[_lib.ptr(t) for t in gs], ins[0].numel(), factor,
                                             epsilon, *[t.data_ptr() for t in outs], _stream(ins[0])))
     return tuple(outs)
+
+
+def quickgelu(x):
+    """model/module.py:15-17: x * sigmoid(1.702 x)."""
+    xs = _f32c(x, "quickgelu")
+    out = torch.empty_like(xs)
+    with torch.cuda.device(xs.device):
+        _lib.check(_lib.lib.iefvad_quickgelu(xs.data_ptr(), xs.numel(), out.data_ptr(), _stream(xs)))
+    return out.to(x.dtype)
 
 
 def relu_bwd(dh, h):

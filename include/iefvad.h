@@ -76,7 +76,9 @@ int iefvad_model_get_plan(const iefvad_model* m);
 int iefvad_model_set_option(iefvad_model* m, const char* name, int64_t value);
 /* Range guard of the 16-bit operand plans (fp16 saturates at 65 504; the reference computes in fp32): every forward
  * ORs bit 0 of a device flag when it produced a non-finite logit - an operand that overflowed anywhere upstream reaches
- * the classifier as inf / NaN.  This call copies the flag to *nonfinite_host, clears it and SYNCHRONISES the stream.
+ * the classifier as inf / NaN.  Bit 1: a valid-rows call with pad de-duplication was given a row map that is not the prefix
+ * map (the valid rows of a chunk must be its first rows; results of that call are undefined).  This call copies the flags
+ * to *nonfinite_host, clears them and SYNCHRONISES the stream.
  * Callers re-run with a bf16 plan (IEFVAD_PLAN_B, fp32's exponent range) or IEFVAD_PLAN_FP32 when it is set. */
 int iefvad_model_check_finite(iefvad_model* m, int* nonfinite_host, void* stream);
 /* rows per internal slab (bounds the activation workspace, ~18 KB per row); default 262144 */
@@ -163,7 +165,7 @@ int iefvad_layernorm(const float* x, int64_t rows, int dim, const float* w1, con
 
 /* nn.Linear with fused epilogue: out = (resid ? resid : 0) + alpha * act(x W^T + bias); act: 0 none, 1 ReLU,
  * 2 QuickGELU (model/module.py:15-17).  x [rows, in_f] fp32, w [out_f, in_f] fp32, out [rows, out_f] fp32.
- * plan: -1 fp32 FFMA, 0 bf16 tcgen05, 1 split-bf16 tcgen05.  tile_n: 0 = heuristic, or 64 / 128 / 256 (one CTA per
+ * plan: -1 fp32 FFMA, 0 bf16 tcgen05, 1 split-bf16 tcgen05, 2 fp16 (E5M10) tcgen05 - the default model plan's GEMM.  tile_n: 0 = heuristic, or 64 / 128 / 256 (one CTA per
  * 128-row tile), or 512 = 256-column tiles on CTA pairs (tcgen05 cta_group::2, 256-row tiles; out_f %% 256 == 0). */
 int iefvad_linear(const float* x, const float* w, const float* bias, const float* resid, float alpha, int act,
                   int64_t rows, int in_f, int out_f, int plan, int tile_n, float* out, void* stream);
@@ -322,6 +324,7 @@ int iefvad_fuse_bwd(const float* mu_i, const float* mu_e, const float* logvar_i,
                     const float* g_wi, const float* g_we, const float* g_mu_i, const float* g_mu_e, const float* g_logvar_i,
                     const float* g_logvar_e, int64_t n, float factor, float epsilon, float* d_mu_i, float* d_mu_e,
                     float* d_logvar_i, float* d_logvar_e, void* stream);
+int iefvad_quickgelu(const float* x, int64_t n, float* out, void* stream);   /* model/module.py:15-17: x * sigmoid(1.702 x) */
 int iefvad_relu_bwd(const float* dh, const float* h, int64_t n, float* out, void* stream);      /* out = h > 0 ? dh : 0 */
 int iefvad_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);                /* y += alpha x */
 int iefvad_outer(const float* a, const float* w, int64_t rows, int dim, float* out, void* stream); /* out[r, c] = a[r] w[c] */

@@ -153,12 +153,15 @@ def test_input_dtypes_and_errors(pkg, full):
             m(img[None].cuda(), ev[None].cuda(), None, None, None)
     finally:
         m.temporal.noise_model = "StudentT"
-    m.train()
+    m.train()                                                   # train() mode: the autograd path (row N3), outputs carry a grad_fn
     try:
-        with pytest.raises(NotImplementedError):
-            m(img[None].cuda(), ev[None].cuda(), None, None, None)
+        out = m(img[None].cuda(), ev[None].cuda(), None, None, None)
+        assert out["logits"].grad_fn is not None and out["image_mu"].shape == (1, 64, 768)
     finally:
         m.eval()
+    out = m(img[None].cuda(), ev[None].cuda(), None, None, None)   # eval() with grad enabled: differentiable, no dropout
+    assert out["logits"].grad_fn is not None
+    assert float((out["logits"].detach() - a).abs().max()) < 2e-3 * float(a.abs().max()) + 1e-4
 
 
 def test_load_state_dict_refreshes_device_weights(pkg, full):

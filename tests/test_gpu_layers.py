@@ -132,3 +132,21 @@ def test_transformer_vs_reference_golden(mods, z, plan):
     assert O.max_norm_err(out_m.cpu().numpy(), z["tr:out_masked"]) < tol
     out_p, _ = tr((x, None))
     assert O.max_norm_err(out_p.cpu().numpy(), z["tr:out_nopad"]) < tol
+
+
+def test_module_layernorm_and_quickgelu_standalone():
+    """model/module.py:7-17 called on their own (inside Transformer they are fused into the block's kernels)."""
+    from iefvad_b200.module import LayerNorm, QuickGELU
+    g = torch.Generator("cpu").manual_seed(9)
+    x = torch.randn(5, 37, 128, generator=g)
+    ln = LayerNorm(128)
+    with torch.no_grad():
+        ln.weight.add_(0.2 * torch.randn(128, generator=g))
+        ln.bias.add_(0.2 * torch.randn(128, generator=g))
+    ref = torch.nn.functional.layer_norm(x.float(), (128,), ln.weight, ln.bias, ln.eps)
+    got = ln.cuda()(x.cuda().half())
+    assert got.dtype == torch.float16 and torch.allclose(got.float().cpu(), ref, atol=4e-3)
+    got32 = ln(x.cuda())
+    assert torch.allclose(got32.cpu(), ref, atol=1e-5)
+    q = QuickGELU()(x.cuda())
+    assert torch.allclose(q.cpu(), x * torch.sigmoid(1.702 * x), atol=1e-6)

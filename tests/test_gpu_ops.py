@@ -20,7 +20,7 @@ def _cuda(a):
 
 
 # tolerance classes (max|x-ref| / max|ref|): fp32 kernels 1e-5; split-bf16 GEMM ~2^-16; plain bf16 GEMM ~2^-8
-TOL = {"fp32": 1e-5, "split": 3e-5, "bf16": 1e-2}
+TOL = {"fp32": 1e-5, "split": 3e-5, "bf16": 1e-2, "fp16": 1.5e-3}    # fp16: 11-bit mantissa operands, 8x finer than bf16
 
 
 @pytest.mark.parametrize("noise,nu", [("StudentT", 8), ("StudentT", 5), ("Gaussian", 8)])
@@ -61,7 +61,7 @@ def test_layernorm_single_and_double(ops, D):
     assert O.max_norm_err(got, ref) < 1e-5
 
 
-@pytest.mark.parametrize("plan", ["fp32", "split", "bf16"])
+@pytest.mark.parametrize("plan", ["fp32", "split", "bf16", "fp16"])
 @pytest.mark.parametrize("rows,in_f,out_f,tile_n", [
     (256, 768, 768, 0), (1000, 768, 2304, 0), (130, 768, 1536, 64), (4096, 768, 768, 128),
     (4096, 768, 768, 256), (1, 768, 768, 0), (257, 128, 96, 0), (300, 3072, 768, 0), (20000, 768, 768, 0),
@@ -79,7 +79,7 @@ def test_linear_plain(ops, plan, rows, in_f, out_f, tile_n):
     assert O.max_norm_err(got, ref) < TOL[plan]
 
 
-@pytest.mark.parametrize("plan", ["fp32", "split", "bf16"])
+@pytest.mark.parametrize("plan", ["fp32", "split", "bf16", "fp16"])
 @pytest.mark.parametrize("act", ["relu", "quickgelu", None])
 @pytest.mark.parametrize("rows,tile_n", [(333, 0), (333, 512), (5000, 512), (5000, 256)])
 def test_linear_epilogue_residual_alpha_act(ops, plan, act, rows, tile_n):

@@ -132,3 +132,25 @@ def test_refresh_weights_after_a_write_through_data(env):
         m.temporal.classifier.bias.add_(1.0)                 # in-place op on the parameter itself: seen automatically
         c = m(img, ev, None, None, None)["logits"].clone()
     assert torch.allclose(b, a + 1.0, atol=1e-5) and torch.allclose(c, a + 2.0, atol=1e-5)
+
+
+def test_pad_dedup_refuses_a_row_map_that_is_not_the_prefix_map(env):
+    """with pad de-duplication the rows past len are assumed to be the zero pads - a row map that selects other
+    rows must be reported, not silently computed on the wrong rows."""
+    m, synth = env
+    m.temporal.precision = "HH"
+    img, ev = synth.make_video(3, 200)
+    ci, ce = synth.chunk_video(img).cuda(), synth.chunk_video(ev).cuda()
+    good = torch.arange(200, dtype=torch.int32, device="cuda")
+    with torch.no_grad():
+        m.temporal.scores(ci, ce, valid_lengths=[200], rowmap=good)
+        assert m.temporal.check_finite()
+        bad = good.clone()
+        bad[100:] += 20                                   # valid rows that are not a prefix of the chunk
+        m.temporal.scores(ci, ce, valid_lengths=[200], rowmap=bad)
+        with pytest.raises(RuntimeError, match="prefix"):
+            m.temporal.check_finite()
+        m.temporal.pad_dedup = False                      # the general path takes any ascending row map
+        out = m.temporal.scores(ci, ce, valid_lengths=[200], rowmap=bad)
+        m.temporal.pad_dedup = True
+        assert m.temporal.check_finite() and torch.isfinite(out["scores"]).all()
