@@ -17,6 +17,7 @@
 #include "model.cuh"
 #include "rank.cuh"
 #include "shaping.cuh"
+#include "outproj_ln.cuh"
 #include "train.cuh"
 
 namespace iefvad {
@@ -121,6 +122,9 @@ int iefvad_model_set_option(iefvad_model* m, const char* name, int64_t value) {
   if (key == "refine_fused") {
     IEF_CHECK(value >= -1 && value <= 1, "refine_fused: -1 (auto), 0 (off), 1 (on)");
     m->impl.refine_fused = int(value);
+  } else if (key == "outproj_ln") {
+    IEF_CHECK(value == 0 || value == 1, "outproj_ln: 0 (separate GEMM + LayerNorm launches) or 1 (one kernel)");
+    m->impl.outproj_ln_mode = int(value);
   } else {
     set_error("iefvad_model_set_option: unknown option '%s'", name);
     return IEFVAD_ERR_INVALID;
@@ -421,6 +425,35 @@ int iefvad_linear(const float* x, const float* w, const float* bias, const float
   g.force_bn = tile_n == 512 ? 256 : tile_n;          // 512 = 256-column tiles on CTA pairs
   g.force_cg = tile_n == 512 ? 2 : (tile_n ? 1 : 0);
   return gemm_tc(g, ep, sms, st);
+}
+
+int iefvad_outproj_ln(const float* ctx, const float* w, const float* bias, const float* resid, const float* ln_w,
+                      const float* ln_b, const float* ln2_w, const float* ln2_b, float eps, int64_t rows,
+                      const int32_t* row_map, void* out_hi_f16, void* out_lo_f16, void* stream) {
+  IEF_CHECK(ctx && w && bias && resid && ln_w && ln_b && out_hi_f16, "iefvad_outproj_ln: null argument");
+  IEF_CHECK(rows >= 0 && rows < (1LL << 31) - 256, "iefvad_outproj_ln: bad row count");
+  if (rows == 0) return IEFVAD_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  constexpr int D = kOutprojLnDim;
+  Scratch sc(st);
+  void *ch, *wh, *rh, *rl, *scr, *idt;
+  IEF_TRY(sc.get(&idt, outproj_ln_identity_bytes()));
+  IEF_TRY(outproj_ln_identity(idt, st));
+  IEF_TRY(sc.get(&ch, size_t(rows) * D * 2));
+  IEF_TRY(sc.get(&wh, size_t(D) * D * 2));
+  IEF_TRY(sc.get(&rh, size_t(rows) * D * 2));
+  IEF_TRY(sc.get(&rl, size_t(rows) * D * 2));
+  IEF_TRY(sc.get(&scr, outproj_ln_scratch_bytes(rows)));
+  IEF_TRY(to_half(ctx, rows * D, ch, sms, st));
+  IEF_TRY(to_half(w, int64_t(D) * D, wh, sms, st));
+  IEF_TRY(ingest(resid, IEFVAD_DT_F32, rows * D, nullptr, (bf16*)rh, (bf16*)rl, sms, st, 1));
+  OutprojLnArgs a;
+  a.ctx = ch; a.w16 = wh; a.bias = bias; a.res_hi = rh; a.res_lo = rl; a.ln_w = ln_w; a.ln_b = ln_b; a.ln2_w = ln2_w;
+  a.ln2_b = ln2_b; a.eps = eps; a.out_hi = out_hi_f16; a.out_lo = out_lo_f16; a.row_map = row_map; a.M = rows; a.scratch = scr;
+  a.identity = idt;
+  return outproj_ln(a, sms, st);
 }
 
 int iefvad_mha(const float* x, const float* in_w, const float* in_b, const float* out_w, const float* out_b,

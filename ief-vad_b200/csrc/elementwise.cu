@@ -63,9 +63,12 @@ ingest_kernel(const Tin* __restrict__ in, long long n8, float* __restrict__ out_
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (hi_fp16) {                          // fp16 operand copy (exact for fp16 inputs), no lo part
-        hi[q] = pack_16x2(v[2 * q], v[2 * q + 1], 1);
-        lo[q] = 0u;
+      if (hi_fp16) {                          // fp16 operand copy (exact for fp16 inputs) + fp16 remainder (zero then)
+        const __half2 h2 = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
+        lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
         continue;
       }
       const bf16 ah = __float2bfloat16_rn(v[2 * q]), bh = __float2bfloat16_rn(v[2 * q + 1]);

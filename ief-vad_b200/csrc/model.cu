@@ -304,6 +304,13 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     // valid-rows mode with >= 2 layers: the producers of the last layer's out-projection inputs write compact rows
     // themselves (LayerNorm of layer L-2: fp32 residual; last attention core: context) - no gather pass
     const bool direct_compact = vr && L >= 2;
+    // Out-projection + residual + LayerNorm(s) as one kernel (outproj_ln.cu) under the all-fp16 plan: y never reaches HBM.
+    // Every encoder stage then works in encoder-row space (all rows, or the packed rows of the pad de-duplication); the
+    // LAST layer's kernel writes its result through the inverse row map, i.e. directly as compact valid rows.
+    static const bool ln_fused_off = [] { const char* e = getenv("IEFVAD_OUTPROJ_LN"); return e && atoi(e) == 0; }();   // A/B knob
+    const bool ln_fused = !fp32_plan && (plan & PLAN_FP16_ATTENTION) && (plan & PLAN_FP16_HEADS) && D == kOutprojLnDim && L >= 1 &&
+                          outproj_ln_mode != 0 && !ln_fused_off &&
+                          (in_dtype == IEFVAD_DT_F16 || !(vr && vr->chunk_start && vr->chunk_valid));
     // Pad de-duplication (valid-rows mode, fp16 inputs, fp16 encoder, chunks of <= 256 rows): the zero-pad rows of a
     // chunk are identical, and stay identical to each other through every row-wise stage and through attention, so
     // ONE representative per chunk goes through the encoder; as an attention key it counts `mult` times (its score
@@ -360,7 +367,14 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       for (const ChunkItem& it : items_host) attn_flops += 4.0 * double(it.rows) * double(it.rows) * D;
     }
     if (dedup && n_items == 0) continue;                 // no valid row in this slab
-    if (direct_compact) {
+    if (ln_fused) {
+      IEF_TRY(ln_scratch.reserve(outproj_ln_scratch_bytes(Me)));
+      if (!ln_ident.p) {
+        IEF_TRY(ln_ident.reserve(outproj_ln_identity_bytes()));
+        IEF_TRY(outproj_ln_identity(ln_ident.p, stream));
+      }
+    }
+    if (direct_compact || (vr && ln_fused)) {
       IEF_TRY(inv_map.reserve(size_t(Me) * sizeof(int)));
       if (dedup) IEF_TRY(inverse_rowmap_items(items_dev.as<ChunkItem>(), aux_dev.as<ChunkAux>(), n_items, inv_map.as<int>(), stream,
                                               (vr->chunk_start && vr->chunk_valid) ? nullptr : vr->rowmap + out0, vr->row_base + row0, status.as<int>()));
@@ -392,7 +406,10 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       } else if (direct16) {
         IEF_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0, "forward: fp16 inputs must be 16-byte aligned");
         x16 = reinterpret_cast<const bf16*>(in);
-      } else
+      } else if (ln_fused)      // the residual stream starts as the fp16 pair (hi = first operand, lo = remainder; 0 for fp16 values)
+        IEF_PROF(KC_INGEST, double(M) * D * (in_esize + 2 + 2), ingest(in, in_dtype, M * D, nullptr, a_hi.as<bf16>(), a_lo.as<bf16>(),
+                       num_sms, stream, 1));
+      else
       IEF_PROF(KC_INGEST, double(M) * D * (in_esize + 4 + 2), ingest(in, in_dtype, M * D, x32.as<float>(), fp32_plan ? nullptr : a_hi.as<bf16>(),
                      esp ? a_lo.as<bf16>() : nullptr, num_sms, stream, (e16 && L > 0) ? 1 : 0));
       for (int i = 0; i < L; ++i) {                                   // model/imf_vad.py:114-116 / :120-122
@@ -425,8 +442,24 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
           at.B = Bs; at.T = int(T); at.H = H; at.dh = dh; at.dhp = dhq; at.Tpad = Tpad;
           if (dedup) { at.B = 1; at.T = int(Me); at.Tpad = int(Me); at.items = items_dev.as<int>(); at.n_chunks = n_items; }
           at.fp16 = a16; at.out_fp16 = a16;
-          if (direct_compact && last) at.row_out = inv_map.as<int>();
+          if (direct_compact && last && !ln_fused) at.row_out = inv_map.as<int>();
           IEF_PROF(KC_ATTN_TC, attn_flops, attn_tc(at, stream));
+          if (ln_fused) {
+            OutprojLnArgs oa;
+            oa.ctx = h_hi.p; oa.w16 = op.w_h16; oa.bias = op.b;
+            oa.res_hi = (i == 0) ? static_cast<const void*>(x16) : a_hi.p;
+            oa.res_lo = (i == 0) ? ((dedup || direct16 || ragged) ? nullptr : a_lo.p) : a_lo.p;
+            oa.ln_w = ln_w[m][i]; oa.ln_b = ln_b[m][i];
+            if (last) { oa.ln2_w = whiten_w[m]; oa.ln2_b = whiten_b[m]; }
+            // in place (each element's residual is read by the warp that later writes it), except the row-mapped result of
+            // the last layer, which lands in other rows: that one goes to h_lo
+            oa.out_hi = (last && vr) ? h_lo.p : a_hi.p;
+            oa.out_lo = last ? nullptr : a_lo.p;
+            oa.row_map = (last && vr) ? inv_map.as<int>() : nullptr;
+            oa.M = Me; oa.scratch = ln_scratch.p; oa.identity = ln_ident.p;
+            IEF_PROF(KC_OUTPROJ_LN, double(Me) * D * (2 + (oa.res_lo ? 4 : 2) + (oa.out_lo ? 4 : 2)), outproj_ln(oa, num_sms, stream));
+            continue;
+          }
           // after the last attention core only the valid rows go on: gather (context, residual) into compact matrices
           const bool compact = vr && last;
           const long long Mc = compact ? Mo : Me;
@@ -476,7 +509,8 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       } else {
         GemmTcArgs gh;
         const bool h16 = (plan & PLAN_FP16_HEADS) != 0;
-        gh.A_hi = a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>(); gh.W_hi = h16 ? heads[m].w_h16 : heads[m].w_hi; gh.W_lo = heads[m].w_lo;
+        gh.A_hi = (ln_fused && vr) ? h_lo.as<bf16>() : a_hi.as<bf16>(); gh.A_lo = a_lo.as<bf16>();
+        gh.W_hi = h16 ? heads[m].w_h16 : heads[m].w_hi; gh.W_lo = heads[m].w_lo;
         gh.M = int(Mo); gh.N = 2 * D; gh.K = D; gh.lda = D; gh.ldw = D;
         gh.nsplit = (!h16 && (plan & PLAN_SPLIT_HEADS)) ? 3 : 1;
         gh.fp16 = h16 ? 1 : 0;
@@ -556,7 +590,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
 
 void Model::destroy() {
   DevBuf* all[] = {&params_f32, &params_hi, &params_lo, &params_h16, &x32, &y32, &a_hi, &a_lo, &h_hi, &h_lo,
-                   &qb, &kb, &vtb, &qkv32, &attn32, &h32, &inv_map, &items_dev, &aux_dev, &status};
+                   &qb, &kb, &vtb, &qkv32, &attn32, &h32, &inv_map, &items_dev, &aux_dev, &status, &ln_scratch, &ln_ident};
   for (DevBuf* b : all) b->release();
 }
 

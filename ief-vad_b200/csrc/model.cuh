@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "outproj_ln.cuh"
 #include "refine.cuh"
 
 namespace iefvad {
@@ -76,6 +77,7 @@ struct Model {
   bool pad_dedup = true;         // valid-rows mode: one representative per chunk for its identical zero-pad rows
   int refine_fused = -1;         // refinement chain as ONE persistent kernel (refine_fused.cu): -1 = when it pays (enough
                                  // rows to fill the CTA pairs), 0 = never (per-step GEMMs), 1 = always
+  int outproj_ln_mode = 1;       // out-projection + residual + LayerNorm(s) as one kernel (outproj_ln.cu) where the plan allows
   bool refine_contig = false;    // the fp16 refinement weights lie back to back (W1_0, W2_0, W1_1, ...) in params_h16
   // evaluation extras (set per call by the C ABI): per-row means of the fusion weights, written at the call's compact offset
   float* eval_wi_mean = nullptr;
@@ -98,7 +100,7 @@ struct Model {
   DevBuf params_f32, params_hi, params_lo, params_h16;
 
   // workspace (one slab)
-  DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32, inv_map, items_dev, aux_dev;
+  DevBuf x32, y32, a_hi, a_lo, h_hi, h_lo, qb, kb, vtb, qkv32, attn32, h32, inv_map, items_dev, aux_dev, ln_scratch, ln_ident;
   DevBuf status;                         // int[4]: [0] bit 0 = a non-finite logit was produced since the last check
   std::vector<ChunkItem> items_host;     // packed-row layout of the current slab (valid-rows mode, see forward)
   std::vector<ChunkAux> aux_host;
@@ -117,7 +119,7 @@ struct Model {
 
 // Per-kernel-class device timing (CUDA events on the launching stream) for bench.py's roofline block.
 enum : int { KC_GEMM_QKV = 0, KC_ATTN_TC, KC_LAYERNORM, KC_FUSE, KC_CLASSIFIER, KC_INGEST, KC_GEMM_SIMT, KC_ATTN_SIMT,
-             KC_GEMM_OUT, KC_GEMM_HEADS, KC_GEMM_REF1, KC_GEMM_REF2, KC_GATHER, KC_REFINE_FUSED, KC_HEADS_FUSE, KC_COUNT };
+             KC_GEMM_OUT, KC_GEMM_HEADS, KC_GEMM_REF1, KC_GEMM_REF2, KC_GATHER, KC_REFINE_FUSED, KC_HEADS_FUSE, KC_OUTPROJ_LN, KC_COUNT };
 struct Profiler {
   bool on = false;
   struct Rec { int cls; double work; cudaEvent_t a, b; };   // work = algorithmic flops (GEMM/attn) or bytes (others)

@@ -54,6 +54,29 @@ def layernorm(x, w1, b1, w2=None, b2=None, eps: float = 1e-5) -> torch.Tensor:
     return out
 
 
+def outproj_ln(ctx, w, bias, resid, ln_w, ln_b, ln2_w=None, ln2_b=None, eps: float = 1e-5, row_map=None, out_rows=None,
+               want_lo: bool = True):
+    """LN2?(LN(resid + ctx @ w.T + bias)) of one encoder layer's tail in one launch (plan HH arithmetic, D = 768).
+    -> (hi, lo): fp16(result) and fp16(result - hi) (lo is None with a row map or want_lo=False).  row_map (int32 [rows]):
+    result row r lands in row row_map[r] of the [out_rows, 768] output, negative entries are dropped."""
+    ctx, w, resid = _f32c(ctx, "outproj_ln"), _f32c(w, "outproj_ln"), _f32c(resid, "outproj_ln")
+    D = ctx.shape[-1]
+    rows = ctx.numel() // D
+    vec = [_f32c(t, "outproj_ln") if t is not None else None for t in (bias, ln_w, ln_b, ln2_w, ln2_b)]
+    if row_map is not None:
+        assert row_map.dtype == torch.int32 and row_map.is_cuda and row_map.numel() == rows
+        hi = torch.zeros((int(out_rows), D), dtype=torch.float16, device=ctx.device)
+        lo = None
+    else:
+        hi = torch.empty((rows, D), dtype=torch.float16, device=ctx.device)
+        lo = torch.empty_like(hi) if want_lo else None
+    with torch.cuda.device(ctx.device):
+        _lib.check(_lib.lib.iefvad_outproj_ln(ctx.data_ptr(), w.data_ptr(), vec[0].data_ptr(), resid.data_ptr(),
+                                              vec[1].data_ptr(), vec[2].data_ptr(), _lib.ptr(vec[3]), _lib.ptr(vec[4]), eps,
+                                              rows, _lib.ptr(row_map), hi.data_ptr(), _lib.ptr(lo), _stream(ctx)))
+    return hi, lo
+
+
 def linear(x, w, bias=None, resid=None, alpha: float = 1.0, act: Optional[str] = None, plan: str = "bf16",
            tile_n: int = 0) -> torch.Tensor:
     """out = (resid or 0) + alpha * act(x @ w.T + bias)."""

@@ -170,6 +170,16 @@ int iefvad_layernorm(const float* x, int64_t rows, int dim, const float* w1, con
 int iefvad_linear(const float* x, const float* w, const float* bias, const float* resid, float alpha, int act,
                   int64_t rows, int in_f, int out_f, int plan, int tile_n, float* out, void* stream);
 
+/* The tail of one temporal-encoder layer as ONE launch (model/imf_vad.py:115-117 / :121-123):
+ *   LN(resid + ctx . w^T + bias; ln_w, ln_b), then LN(.; ln2_w, ln2_b) when ln2_w / ln2_b are non-NULL (the whitening
+ * LayerNorm after the last layer).  Plan HH's arithmetic: ctx and w rounded to fp16, fp32 accumulation, resid carried as an
+ * fp16 hi + lo pair, LayerNorm statistics in fp32.  ctx, resid [rows, 768], w [768, 768] ([out, in]) fp32 device tensors.
+ * out_hi_f16 receives fp16(result); out_lo_f16 (optional) fp16(result - hi).  row_map (optional, device, [rows]): result
+ * row r goes to row row_map[r] of out_hi_f16 (negative: dropped); out_lo_f16 must be NULL then. */
+int iefvad_outproj_ln(const float* ctx, const float* w, const float* bias, const float* resid, const float* ln_w,
+                      const float* ln_b, const float* ln2_w, const float* ln2_b, float eps, int64_t rows,
+                      const int32_t* row_map, void* out_hi_f16, void* out_lo_f16, void* stream);
+
 /* nn.MultiheadAttention(batch_first=True)(x, x, x)[0] in eval mode (model/imf_vad.py:115; torch/nn/functional.py:6244).
  * x [B, T, D] fp32; in_w [3D, D], in_b [3D], out_w [D, D], out_b [D].  attn_mask: optional additive [T, T] fp32;
  * key_padding_mask: optional [B, T] uint8 (non-zero = ignore).  plan as for iefvad_linear. */
