@@ -4,11 +4,11 @@
 // and both launches are HBM-bound; here y never leaves tensor memory: 8 bytes per element (context and residual in,
 // the 16-bit result (pair) out).
 //
-// * The residual is added BY THE TENSOR CORE: after the 12 k-blocks of ctx . Wo^T the same accumulator takes 4 (8 with a
-//   remainder part) more k-blocks  x[:, tile columns] . I^T  with a 256 x 256 fp16 identity as the W operand - exact (every
-//   product is x * 1 or x * 0, fp32 accumulation) and the tensor pipe has the time (the kernel is HBM-bound), while the
-//   CUDA cores, which bound the first version of this kernel, lose a shared-memory ring, two conversions and two additions
-//   per element.
+// * The residual is added BY THE TENSOR CORE: after the 12 k-blocks of ctx . Wo^T the accumulator takes 4 (8 with a
+//   remainder part) more k-blocks  x[:, 64 tile columns] . I_64^T  into the 64 accumulator columns they belong to (N = 64
+//   MMAs with a 64 x 64 fp16 identity as the W operand) - exact (every product is x * 1 or x * 0, fp32 accumulation) and
+//   the tensor pipe has the time, while the CUDA cores, which bound the first version of this kernel, lose a
+//   shared-memory ring, two conversions and two additions per element.
 // * A LayerNorm row spans all 768 output columns but an accumulator tile is 256 columns wide (a CTA pair owns 256 rows x
 //   256 columns, cta_group::2, fp32 accumulators = half of TMEM, double-buffered).  So THREE pairs - a "group" - work on
 //   the three column tiles of the same 256-row block at the same time: they are ONE CLUSTER of 6 CTAs and exchange
@@ -27,6 +27,7 @@
 //   mean(u^2), mean(u b1) follow from the sums of w d, w^2 d, w^2 d^2, w b1 d (d = y - shift) gathered in pass 1 once mu
 //   is known.
 // Per-row results do not depend on the tile position or the batch size.
+#include <cstdlib>
 #include <cstring>
 
 #include "outproj_ln.cuh"
@@ -57,7 +58,8 @@ constexpr uint32_t kConstBytes = 128;            // per-part sums of the LayerNo
 constexpr uint32_t kSmemLimit = 232448;
 constexpr int kClusterCtas = 2 * kNT;             // three CTA pairs
 constexpr int kKBMain = D / BK;                  // k-blocks of ctx . Wo^T
-constexpr int kKBRes = BN / BK;                  // k-blocks of x[:, tile columns] . I^T
+constexpr int kKBRes = BN / BK;                  // k-blocks of x[:, 64 tile columns] . I_64^T
+constexpr uint32_t kIBytes = (BK / 2) * BK * 2;  // this CTA's half (32 rows) of the 64 x 64 identity
 
 struct LnParams {
   const float* bias;
@@ -71,6 +73,7 @@ struct LnParams {
   int groups;          // blocks in flight (grid = groups * kNT pairs)
   int stages;
   uint32_t warp_bytes;
+  int dbg;             // IEFVAD_OUTPROJ_LN_DBG bits (timing experiments only): 1 = no residual k-blocks, 2 = no epilogue math, 8 = L2 prefetch
   const int* row_map;
   __half* out_hi;      // row-mapped stores only
 };
@@ -95,7 +98,7 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, float4 v, uint32_t mb
 
 __global__ void outproj_ln_identity_kernel(__half* ident) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < BN * BN) ident[i] = __float2half_rn((i / BN) == (i % BN) ? 1.f : 0.f);
+  if (i < BK * BK) ident[i] = __float2half_rn((i / BK) == (i % BK) ? 1.f : 0.f);
 }
 
 // TWO: a second (whitening) LayerNorm follows; RES_LO: the residual has a remainder part; OUT_LO: so has the result
@@ -128,7 +131,7 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
   const uint32_t lead = crank & ~1u;                                 // the pair's leader CTA
   const int grp = blockIdx.x / kClusterCtas;
   const int n_blk = int(crank >> 1);
-  constexpr int kKB = kKBMain + kKBRes * (1 + RES_LO);
+  const int kKB = (p.dbg & 1) ? kKBMain : kKBMain + kKBRes * (1 + RES_LO);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&ta);
@@ -167,16 +170,21 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + size_t(s) * kStageBytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), lead);
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kStageBytes);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], kb < kKBMain ? 2 * kStageBytes : 2 * (kABytes + kIBytes));
+          const int m_next = m_blk + 2 * p.groups;
+          const bool pf = (p.dbg & 8) && mp + p.groups < p.num_mp;      // A/B knob: L2 prefetch of the next tile's A boxes (measured no gain)
           if (kb < kKBMain) {
             tma_load_2d_cg2(&ta, lead_full, sa, kb * BK, m_blk * BM);
             tma_load_2d_cg2(&tw, lead_full, sa + kABytes, kb * BK, n_blk * BN + int(rank) * (BN / 2));
+            if (pf) tma_prefetch_2d(&ta, kb * BK, m_next * BM);
           } else {
             // residual block: A = x[rows, tile columns kk * 64 ..], W = this CTA's rows of the identity
             const int kr = kb - kKBMain;
             const int kk = kr & (kKBRes - 1);
-            tma_load_2d_cg2((RES_LO && kr >= kKBRes) ? &trl : &trh, lead_full, sa, n_blk * BN + kk * BK, m_blk * BM);
-            tma_load_2d_cg2(&tid, lead_full, sa + kABytes, kk * BK, int(rank) * (BN / 2));
+            const CUtensorMap* tr = (RES_LO && kr >= kKBRes) ? &trl : &trh;
+            tma_load_2d_cg2(tr, lead_full, sa, n_blk * BN + kk * BK, m_blk * BM);
+            tma_load_2d_cg2(&tid, lead_full, sa + kABytes, 0, int(rank) * (BK / 2));
+            if (pf) tma_prefetch_2d(tr, n_blk * BN + kk * BK, m_next * BM);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -186,6 +194,7 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
     // ===================== MMA issuer (leader CTA) =====================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
+      constexpr uint32_t idesc_res = make_idesc_f16(2 * BM, BK);
       const uint16_t pair_mask = uint16_t(3u << lead);
       int s = 0;
       uint32_t ph = 0;
@@ -202,9 +211,16 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
           const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + kABytes);
+          if (kb < kKBMain) {
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4)
-            umma_bf16_cg2(d_tmem, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < BK / 16; ++k4)
+              umma_bf16_cg2(d_tmem, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
+          } else {
+            const uint32_t d_res = d_tmem + uint32_t(((kb - kKBMain) & (kKBRes - 1)) * BK);     // the 64 columns this block adds to
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4)
+              umma_bf16_cg2(d_res, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc_res, 1u);
+          }
           tc_commit_cg2(&empty[s], pair_mask);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -274,6 +290,12 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
       mbar_wait(&tfull[team], aph);
       tc_fence_after();
       float v[32];
+      if (p.dbg & 2) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[team]), lead));
+        continue;
+      }
 
       // ---- pass 1: y = acc (= ctx . Wo^T + x) + bias, back into TMEM; shifted sums of this thread's 128 columns
       float shift = 0.f, S1 = 0.f, S2 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f, A4 = 0.f;
@@ -460,11 +482,11 @@ long long padded_rows(long long M) { return (M + 255) / 256 * 256; }
 
 size_t outproj_ln_scratch_bytes(long long) { return 16; }   // the exchange lives in distributed shared memory now
 
-size_t outproj_ln_identity_bytes() { return size_t(BN) * BN * sizeof(__half); }
+size_t outproj_ln_identity_bytes() { return size_t(BK) * BK * sizeof(__half); }
 
 int outproj_ln_identity(void* ident, cudaStream_t stream) {
   IEF_CHECK(ident, "outproj_ln_identity: null buffer");
-  outproj_ln_identity_kernel<<<(BN * BN + 255) / 256, 256, 0, stream>>>(static_cast<__half*>(ident));
+  outproj_ln_identity_kernel<<<(BK * BK + 255) / 256, 256, 0, stream>>>(static_cast<__half*>(ident));
   IEF_CUDA(cudaGetLastError());
   count_launches(1);
   return IEFVAD_OK;
@@ -489,6 +511,9 @@ int outproj_ln(const OutprojLnArgs& a, int num_sms, cudaStream_t stream) {
   const uint32_t fixed = 1024 + kEpiWarps * p.warp_bytes + kParamBytes + kConstBytes + xch_bytes + kBarBytes;
   p.stages = int((kSmemLimit - fixed) / kStageBytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  static const int dbg = [] { const char* e = getenv("IEFVAD_OUTPROJ_LN_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg & 15;
+  if ((dbg >> 4) > 0 && (dbg >> 4) < p.stages) p.stages = dbg >> 4;     // bits 4+: cap on the operand ring depth
   IEF_CHECK(p.stages >= 2, "outproj_ln: no room for the operand ring");
   const size_t smem_bytes = fixed + size_t(p.stages) * kStageBytes;
   p.row_map = a.row_map;
@@ -500,7 +525,7 @@ int outproj_ln(const OutprojLnArgs& a, int num_sms, cudaStream_t stream) {
   IEF_TRY(make_tmap_2d(&trh, a.res_hi, D, uint64_t(a.M), uint64_t(D) * 2, BK, BM));
   if (a.res_lo) IEF_TRY(make_tmap_2d(&trl, a.res_lo, D, uint64_t(a.M), uint64_t(D) * 2, BK, BM));
   else trl = trh;
-  IEF_TRY(make_tmap_2d(&tid, a.identity, BN, BN, uint64_t(BN) * 2, BK, BN / 2));
+  IEF_TRY(make_tmap_2d(&tid, a.identity, BK, BK, uint64_t(BK) * 2, BK, BK / 2));
   if (!a.row_map) IEF_TRY(make_tmap_2d(&toh, a.out_hi, D, uint64_t(a.M), uint64_t(D) * 2, CW, 32, TM_BF16, TM_SWIZZLE_64B));
   else toh = trh;
   if (a.out_lo) IEF_TRY(make_tmap_2d(&tol, a.out_lo, D, uint64_t(a.M), uint64_t(D) * 2, CW, 32, TM_BF16, TM_SWIZZLE_64B));

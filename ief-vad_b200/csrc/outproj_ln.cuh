@@ -24,7 +24,7 @@ struct OutprojLnArgs {
                                    // out_lo must be null then
   long long M = 0;
   void* scratch = nullptr;         // >= outproj_ln_scratch_bytes(M) (partial row statistics + arrival counters)
-  const void* identity = nullptr;  // fp16 [256, 256] identity (outproj_ln_identity): the W operand that adds the residual
+  const void* identity = nullptr;  // fp16 [64, 64] identity (outproj_ln_identity): the W operand that adds the residual
 };
 
 size_t outproj_ln_scratch_bytes(long long M);
