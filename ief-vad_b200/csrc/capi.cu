@@ -122,6 +122,9 @@ int iefvad_model_set_option(iefvad_model* m, const char* name, int64_t value) {
   if (key == "refine_fused") {
     IEF_CHECK(value >= -1 && value <= 1, "refine_fused: -1 (auto), 0 (off), 1 (on)");
     m->impl.refine_fused = int(value);
+  } else if (key == "heads_fuse") {
+    IEF_CHECK(value == 0 || value == 1, "heads_fuse: 0 (heads GEMMs + fusion kernel) or 1 (one kernel)");
+    m->impl.heads_fuse_mode = int(value);
   } else if (key == "outproj_ln") {
     IEF_CHECK(value == 0 || value == 1, "outproj_ln: 0 (separate GEMM + LayerNorm launches) or 1 (one kernel)");
     m->impl.outproj_ln_mode = int(value);
@@ -278,9 +281,11 @@ static int forward_from_host(iefvad_model* m, const void* img_host, const void* 
       if (m->ex_wide[i]) o[i] = m->ex_wide[i] + o0 * D;               // the caller wants this tensor: write it there
     m->impl.eval_wi_mean = m->ex_wi_mean ? m->ex_wi_mean + o0 : nullptr;
     m->impl.eval_we_mean = m->ex_we_mean ? m->ex_we_mean + o0 : nullptr;
+    m->impl.heads_outputs_unused = !m->ex_wide[1] && !m->ex_wide[2];      // mu / logvar land in scratch: nobody reads them
     const int frc = m->impl.forward(m->host_in[buf][0].p, m->host_in[buf][1].p, in_dtype, Bs, T, o[0], ldev + o0, o[1], o[2], o[3],
                                     o[4], nullptr, nullptr, sdev ? sdev + o0 : nullptr, st, valid_len_host ? &vr : nullptr);
     m->impl.eval_wi_mean = m->impl.eval_we_mean = nullptr;
+    m->impl.heads_outputs_unused = false;
     IEF_TRY(frc);
     j0 += nvalid;
     IEF_CUDA(cudaEventRecord(m->ev_consumed[buf], st));
@@ -342,9 +347,11 @@ int iefvad_model_forward_scores(iefvad_model* m, const void* img, const void* ev
     if (m->ex_wide[i]) o[i] = m->ex_wide[i];
   m->impl.eval_wi_mean = m->ex_wi_mean;
   m->impl.eval_we_mean = m->ex_we_mean;
+  m->impl.heads_outputs_unused = !m->ex_wide[1] && !m->ex_wide[2];
   const int rc = m->impl.forward(img, ev, in_dtype, B, T, o[0], logits, o[1], o[2], o[3], o[4], nullptr, nullptr, scores, st,
                                  valid_len_host ? &vr : nullptr);
   m->impl.eval_wi_mean = m->impl.eval_we_mean = nullptr;
+  m->impl.heads_outputs_unused = false;
   return rc;
 }
 

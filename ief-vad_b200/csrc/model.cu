@@ -367,6 +367,11 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       for (const ChunkItem& it : items_host) attn_flops += 4.0 * double(it.rows) * double(it.rows) * D;
     }
     if (dedup && n_items == 0) continue;                 // no valid row in this slab
+    // heads of both modalities + fusion as one kernel (heads_fuse.cu) when the caller keeps neither mu / logvar nor the fusion
+    // weights (the evaluation forward) and the refinement chain takes the fp16 pair
+    static const bool heads_fuse_off = [] { const char* e = getenv("IEFVAD_HEADS_FUSE"); return e && atoi(e) == 0; }();   // A/B knob
+    const bool hf = ln_fused && vr && heads_outputs_unused && !w_i && !eval_wi_mean && (plan & PLAN_FP16_REFINE) && R > 0 &&
+                    D == kHeadsFuseDim && L >= 2 && heads_fuse_mode != 0 && !heads_fuse_off;
     if (ln_fused) {
       IEF_TRY(ln_scratch.reserve(outproj_ln_scratch_bytes(Me)));
       if (!ln_ident.p) {
@@ -453,7 +458,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
             if (last) { oa.ln2_w = whiten_w[m]; oa.ln2_b = whiten_b[m]; }
             // in place (each element's residual is read by the warp that later writes it), except the row-mapped result of
             // the last layer, which lands in other rows: that one goes to h_lo
-            oa.out_hi = (last && vr) ? h_lo.p : a_hi.p;
+            oa.out_hi = (last && vr) ? ((hf && m == 0) ? x32.p : h_lo.p) : a_hi.p;   // heads_fuse: image rows wait in x32 (as fp16)
             oa.out_lo = last ? nullptr : a_lo.p;
             oa.row_map = (last && vr) ? inv_map.as<int>() : nullptr;
             oa.M = Me; oa.scratch = ln_scratch.p; oa.identity = ln_ident.p;
@@ -503,7 +508,7 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
       EpiParams eh;
       eh.bias = heads[m].b; eh.out_f32 = mu_out[m] + out0 * D; eh.out_f32_b = lv_out[m] + out0 * D; eh.ld_f32 = D;
       eh.split_col = D;
-      if (Mo == 0) continue;
+      if (Mo == 0 || hf) continue;
       if (fp32_plan) {
         IEF_PROF(KC_GEMM_SIMT, 4.0 * Mo * D * D, gemm_simt(x32.as<float>(), D, heads[m].w, D, int(Mo), 2 * D, D, eh, stream));
       } else {
@@ -526,7 +531,12 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
     // refinement step moves 7.5 KB per row through HBM instead of 12 KB (no separate fp32 copy of x)
     const bool pair16 = r16 && R > 0;
     float* xcur = (R == 0) ? fused_out : (pair16 ? nullptr : x32.as<float>());
-    {
+    if (hf) {
+      HeadsFuseArgs ha;
+      ha.x_i = x32.p; ha.x_e = h_lo.p; ha.w_i16 = heads[0].w_h16; ha.w_e16 = heads[1].w_h16; ha.b_i = heads[0].b; ha.b_e = heads[1].b;
+      ha.factor = factor; ha.eps = eps; ha.out_hi = a_hi.p; ha.out_lo = a_lo.p; ha.M = Mo;
+      IEF_PROF(KC_HEADS_FUSE, 8.0 * Mo * D * D, heads_fuse(ha, num_sms, stream));
+    } else {
       bf16* f_hi = (fp32_plan || R == 0) ? nullptr : a_hi.as<bf16>();
       bf16* f_lo = ((rsp || pair16) && R > 0) ? a_lo.as<bf16>() : nullptr;
       const double fuse_bytes = double(Mo) * D * (16 + (w_i ? 8 : 0) + (xcur ? 4 : 0) + (f_hi ? 2 : 0) + (f_lo ? 2 : 0));

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "heads_fuse.cuh"
 #include "outproj_ln.cuh"
 #include "refine.cuh"
 
@@ -77,6 +78,8 @@ struct Model {
   bool pad_dedup = true;         // valid-rows mode: one representative per chunk for its identical zero-pad rows
   int refine_fused = -1;         // refinement chain as ONE persistent kernel (refine_fused.cu): -1 = when it pays (enough
                                  // rows to fill the CTA pairs), 0 = never (per-step GEMMs), 1 = always
+  int heads_fuse_mode = 1;       // heads of both modalities + fusion as one kernel (heads_fuse.cu) when mu / logvar are not kept
+  bool heads_outputs_unused = false;   // set per call by the C ABI: the mu / logvar / w pointers of forward() are scratch
   int outproj_ln_mode = 1;       // out-projection + residual + LayerNorm(s) as one kernel (outproj_ln.cu) where the plan allows
   bool refine_contig = false;    // the fp16 refinement weights lie back to back (W1_0, W2_0, W1_1, ...) in params_h16
   // evaluation extras (set per call by the C ABI): per-row means of the fusion weights, written at the call's compact offset

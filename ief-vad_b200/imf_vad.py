@@ -49,6 +49,9 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         # refinement chain as one persistent kernel: None = when the batch is large enough (library default), False /
         # True = never / always (both forms produce identical bits; iefvad_model_set_option "refine_fused")
         self.refine_fused = None
+        # fused encoder tails / heads (csrc/outproj_ln.cu, heads_fuse.cu); False = the separate GEMM + row-wise launches
+        self.outproj_ln = True
+        self.heads_fuse = True
         # range guard of the 16-bit plans: "raise" (default) = check_finite() / Evaluator.finish() raise when a forward
         # produced a non-finite logit; "fallback" = the Evaluator re-runs the pass under the bf16 plan "B"
         self.on_overflow = os.environ.get("IEFVAD_ON_OVERFLOW", "raise")
@@ -164,6 +167,8 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         mode = -1 if self.refine_fused is None else (int(self.refine_fused) if not isinstance(self.refine_fused, bool)
                                                      else int(self.refine_fused))
         _lib.check(_lib.lib.iefvad_model_set_option(h, b"refine_fused", mode))
+        _lib.check(_lib.lib.iefvad_model_set_option(h, b"outproj_ln", int(bool(self.outproj_ln))))
+        _lib.check(_lib.lib.iefvad_model_set_option(h, b"heads_fuse", int(bool(self.heads_fuse))))
 
     def _sync_params(self, handle: int, device: torch.device, stream: int) -> None:
         """Upload parameters whose storage or version changed since the last forward (load_state_dict,
@@ -271,7 +276,7 @@ class MultiModal_Fusion_Attn_Iter(nn.Module):
         limit = int(os.environ.get("IEFVAD_GRAPH_ROWS", "2048") or 0)
         if B * T > limit or torch.cuda.is_current_stream_capturing():
             return None
-        key = (str(device), B, T, img.dtype, plan, bool(with_scores), self.refine_fused)
+        key = (str(device), B, T, img.dtype, plan, bool(with_scores), self.refine_fused, self.outproj_ln, self.heads_fuse)
         cache = self.__dict__.setdefault("_graphs", {})
         entry = cache.get(key)
         if entry is False:
