@@ -8,7 +8,9 @@
 // Same arithmetic, instruction for instruction, as gemm_tc (fp16 operands, fp32 accumulation in k order, + bias) followed
 // by fuse_kernel (expf, IEEE division, separately rounded products): the pair is bit-identical to the three-launch form.
 // TMEM is full (2 x 256 columns), so the epilogue of a tile does not overlap the MMAs of the next one - but the operand ring
-// (6 stages) refills meanwhile, and the kernel still moves a sixth of the bytes.
+// (6 stages) refills meanwhile, and the kernel still moves a sixth of the bytes.  Sixteen epilogue warps (four per scheduler,
+// one 32-feature chunk each, 8 features at a time to stay inside 96 registers) keep that exposed epilogue short: it is bound
+// by the CUDA cores (expf and IEEE division per element).
 #include <cstring>
 
 #include "heads_fuse.cuh"
@@ -25,14 +27,14 @@ constexpr int BF = 128;                          // features per tile
 constexpr int BK = 64;
 constexpr int CW = 32;
 constexpr int kFB = D / BF;                      // feature blocks
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kBBytes = (BN / 2) * BK * 2;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kBox16 = 32 * CW * 2;
-constexpr uint32_t kWarpBytes = 2 * kBox16;      // hi + lo boxes
+constexpr uint32_t kWarpBytes = kBox16;          // one box per warp: the hi part leaves, then the lo part
 constexpr uint32_t kBarBytes = 256;
 constexpr uint32_t kSmemLimit = 232448;
 constexpr int kKB = D / BK;                      // k-blocks per modality
@@ -139,12 +141,11 @@ heads_fuse_kernel(const __grid_constant__ CUtensorMap txi, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue: 8 warps, thread == row =====================
+    // ===================== epilogue: 16 warps, thread == row =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int par = ew >> 2;               // 32-feature chunks par and par + 2 of the tile's four
-    uint8_t* Hb = epi_base + size_t(ew) * kWarpBytes;
-    uint8_t* Lb = Hb + kBox16;
+    const int c32 = ew >> 2;               // this warp's 32-feature chunk of the tile
+    uint8_t* Bx = epi_base + size_t(ew) * kWarpBytes;
     if (lane == 0) {
       tma_prefetch_desc(&toh);
       tma_prefetch_desc(&tol);
@@ -156,77 +157,78 @@ heads_fuse_kernel(const __grid_constant__ CUtensorMap txi, const __grid_constant
       const int row0 = m_blk * BM + quarter * 32;
       mbar_wait(tfull, uint32_t(it & 1));
       tc_fence_after();
-#pragma unroll 1
-      for (int jj = 0; jj < 2; ++jj) {
-        const int c32 = par + 2 * jj;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          const int fo = c32 * CW + half * 16;               // feature offset inside the tile
-          float mi[16], li[16], me[16], le[16];
-          tmem_ld16(t0 + uint32_t(fo), mi);
-          tmem_ld16(t0 + uint32_t(BF + fo), li);
-          tmem_ld16(t0 + uint32_t(BN + fo), me);
-          tmem_ld16(t0 + uint32_t(BN + BF + fo), le);
-          const int f0 = fb * BF + fo;
-          float4 bmi[4], bli[4], bme[4], ble[4];
+      uint32_t lo_keep[16];                                  // the remainder halves wait in registers for the box
+      if (lane == 0) bulk_wait_read<0>();                    // the previous tile's lo store has read the box
+      __syncwarp();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            bmi[g] = __ldg(reinterpret_cast<const float4*>(p.b_i + f0) + g);
-            bli[g] = __ldg(reinterpret_cast<const float4*>(p.b_i + D + f0) + g);
-            bme[g] = __ldg(reinterpret_cast<const float4*>(p.b_e + f0) + g);
-            ble[g] = __ldg(reinterpret_cast<const float4*>(p.b_e + D + f0) + g);
-          }
-          tmem_ld_wait();
-          if (jj == 1 && half == 1) {                        // both accumulators fully read: the next tile's MMAs may start
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tempty), 0));
-          }
-          if (half == 0) {
-            if (lane == 0) bulk_wait_read<0>();              // the previous chunk's stores have read the boxes
-            __syncwarp();
-          }
-          float f[16];
+      for (int step = 0; step < 4; ++step) {
+        const int fo = c32 * CW + step * 8;                  // feature offset inside the tile
+        float mi[8], li[8], me[8], le[8];
+        tmem_ld8(t0 + uint32_t(fo), mi);
+        tmem_ld8(t0 + uint32_t(BF + fo), li);
+        tmem_ld8(t0 + uint32_t(BN + fo), me);
+        tmem_ld8(t0 + uint32_t(BN + BF + fo), le);
+        const int f0 = fb * BF + fo;
+        float4 bmi[2], bli[2], bme[2], ble[2];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float b0[4] = {bmi[g].x, bmi[g].y, bmi[g].z, bmi[g].w}, b1[4] = {bli[g].x, bli[g].y, bli[g].z, bli[g].w};
-            const float b2[4] = {bme[g].x, bme[g].y, bme[g].z, bme[g].w}, b3[4] = {ble[g].x, ble[g].y, ble[g].z, ble[g].w};
+        for (int g = 0; g < 2; ++g) {
+          bmi[g] = __ldg(reinterpret_cast<const float4*>(p.b_i + f0) + g);
+          bli[g] = __ldg(reinterpret_cast<const float4*>(p.b_i + D + f0) + g);
+          bme[g] = __ldg(reinterpret_cast<const float4*>(p.b_e + f0) + g);
+          ble[g] = __ldg(reinterpret_cast<const float4*>(p.b_e + D + f0) + g);
+        }
+        tmem_ld_wait();
+        if (step == 3) {                                     // both accumulators fully read: the next tile's MMAs may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tempty), 0));
+        }
+        float f[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = g * 4 + e;
-              // exact op order of model/imf_vad.py:134-144 (== fuse_kernel), every product / sum rounded separately
-              const float mui = __fadd_rn(mi[i], b0[e]), lvi = __fadd_rn(li[i], b1[e]);
-              const float mue = __fadd_rn(me[i], b2[e]), lve = __fadd_rn(le[i], b3[e]);
-              const float ri = __fmul_rn(p.factor, expf(-lvi));
-              const float re = __fmul_rn(p.factor, expf(-lve));
-              const float den = __fadd_rn(__fadd_rn(ri, re), p.eps);
-              const float wi = __fdiv_rn(ri, den), we = __fdiv_rn(re, den);
-              f[i] = __fadd_rn(__fmul_rn(wi, mui), __fmul_rn(we, mue));
-            }
-          }
+        for (int g = 0; g < 2; ++g) {
+          const float b0[4] = {bmi[g].x, bmi[g].y, bmi[g].z, bmi[g].w}, b1[4] = {bli[g].x, bli[g].y, bli[g].z, bli[g].w};
+          const float b2[4] = {bme[g].x, bme[g].y, bme[g].z, bme[g].w}, b3[4] = {ble[g].x, ble[g].y, ble[g].z, ble[g].w};
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float a = f[g * 8 + 2 * q], b = f[g * 8 + 2 * q + 1];
-              const __half2 h2 = __floats2half2_rn(a, b);
-              hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
-              lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
-            *reinterpret_cast<uint4*>(Hb + sw64(lane, half * 2 + g)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(Lb + sw64(lane, half * 2 + g)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int e = 0; e < 4; ++e) {
+            const int i = g * 4 + e;
+            // exact op order of model/imf_vad.py:134-144 (== fuse_kernel), every product / sum rounded separately
+            const float mui = __fadd_rn(mi[i], b0[e]), lvi = __fadd_rn(li[i], b1[e]);
+            const float mue = __fadd_rn(me[i], b2[e]), lve = __fadd_rn(le[i], b3[e]);
+            const float ri = __fmul_rn(p.factor, expf(-lvi));
+            const float re = __fmul_rn(p.factor, expf(-lve));
+            const float den = __fadd_rn(__fadd_rn(ri, re), p.eps);
+            const float wi = __fdiv_rn(ri, den), we = __fdiv_rn(re, den);
+            f[i] = __fadd_rn(__fmul_rn(wi, mui), __fmul_rn(we, mue));
           }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&toh, Hb, fb * BF + c32 * CW, row0);
-          tma_store_2d(&tol, Lb, fb * BF + c32 * CW, row0);
-          bulk_commit();
+        uint32_t hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = f[2 * q], b = f[2 * q + 1];
+          const __half2 h2 = __floats2half2_rn(a, b);
+          hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+          const float2 hf = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+          lo_keep[step * 4 + q] = *reinterpret_cast<const uint32_t*>(&l2);
         }
+        *reinterpret_cast<uint4*>(Bx + sw64(lane, step)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&toh, Bx, fb * BF + c32 * CW, row0);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(Bx + sw64(lane, g)) = make_uint4(lo_keep[g * 4], lo_keep[g * 4 + 1], lo_keep[g * 4 + 2], lo_keep[g * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tol, Bx, fb * BF + c32 * CW, row0);
+        bulk_commit();
       }
     }
     if (lane == 0) bulk_wait_all<0>();
