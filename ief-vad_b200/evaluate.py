@@ -225,8 +225,21 @@ class Evaluator:
         """AUC / AP overall, Ano-AUC and class-wise AUC / AP from one ranking pass; the [num_subsets, 4] table is
         copied to pinned host memory on the stream - nothing here waits for the device."""
         table = ops.auc_ap_multi(scores, self.pos, self.member, self.num_subsets, self.repeat)
-        host = torch.empty(table.shape, dtype=table.dtype, pin_memory=True)
+        # a ring of pinned tables: a fresh pinned allocation per pass is a cudaHostAlloc whenever the previous ones are still
+        # in flight (a loop of asynchronous passes), which serialises host and device
+        ring = self.__dict__.setdefault("_table_ring", [])
+        i = self.__dict__.get("_table_i", 0)
+        self._table_i = i + 1
+        if len(ring) < 64:
+            ring.append([torch.empty(table.shape, dtype=table.dtype, pin_memory=True), torch.cuda.Event()])
+            host, done = ring[-1]
+        else:
+            host, done = ring[i % 64]
+            done.synchronize()                      # the copy of 64 passes ago (long finished unless the caller never syncs)
+            if host.shape != table.shape:
+                host = ring[i % 64][0] = torch.empty(table.shape, dtype=table.dtype, pin_memory=True)
         host.copy_(table, non_blocking=True)
+        done.record(torch.cuda.current_stream(self.device))
         return host
 
     def finish(self, host_table: torch.Tensor) -> Dict[str, object]:
