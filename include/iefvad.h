@@ -72,7 +72,12 @@ int iefvad_model_set_plan(iefvad_model* m, int plan);
 int iefvad_model_get_plan(const iefvad_model* m);
 /* Tuning / test knobs by name.  "refine_fused": the refinement chain (model/imf_vad.py:146-149) as ONE persistent kernel
  * whose hidden activations never leave the SM: -1 = when the batch fills the CTA pairs (default), 0 = never (two tcgen05
- * GEMM launches per step), 1 = always.  Both forms give identical bits. */
+ * GEMM launches per step), 1 = always.  Both forms give identical bits.
+ * "outproj_ln" (default 1): an encoder layer's tail LN(x + out_proj(ctx)) [+ the whitening LayerNorm] (model/imf_vad.py:115-117)
+ * as ONE kernel under the all-fp16 plan; 0 = GEMM + LayerNorm launches (results agree to fp32 statistics rounding).
+ * "heads_fuse" (default 1): mu / logvar heads of both modalities + fusion (model/imf_vad.py:125-144) as ONE kernel on the
+ * evaluation path, used when the call keeps neither mu / logvar nor the fusion weights; 0 = heads GEMMs + fusion kernel
+ * (identical bits). */
 int iefvad_model_set_option(iefvad_model* m, const char* name, int64_t value);
 /* Range guard of the 16-bit operand plans (fp16 saturates at 65 504; the reference computes in fp32): every forward
  * ORs bit 0 of a device flag when it produced a non-finite logit - an operand that overflowed anywhere upstream reaches
