@@ -1,4 +1,5 @@
 // The IEF-VAD forward (model/imf_vad.py:109-161) as a sequence of sm_100a kernels.
+#include <nvtx3/nvToolsExt.h>
 #include "model.cuh"
 
 #include <algorithm>
@@ -74,12 +75,21 @@ int Profiler::read(double* ms, double* work, long long* launches) {
 }
 
 // time one launch when profiling is on (no-op otherwise)
-#define IEF_PROF(cls, work, call)          \
-  do {                                     \
-    profiler().begin(cls, work, stream);   \
-    int _prc = (call);                     \
-    profiler().end(stream);                \
-    if (_prc != 0) return _prc;            \
+// NVTX ranges around every stage of the forward (nsys / ncu --nvtx timelines; SURVEY section 5 tracing row).  NVTX v3 is
+// header-only: without an attached tool the calls are no-ops, and they are compiled in only behind IEFVAD_NVTX=1.
+static const bool g_nvtx = [] { const char* e = getenv("IEFVAD_NVTX"); return e && atoi(e) != 0; }();
+static const char* const kClassNames[KC_COUNT] = {"gemm_qkv", "attn_tc", "layernorm", "fuse", "classifier", "ingest", "gemm_simt",
+                                                  "attn_simt", "gemm_out_proj", "gemm_heads", "gemm_refine1", "gemm_refine2",
+                                                  "gather_valid_rows", "refine_fused", "heads_fuse", "outproj_ln"};
+
+#define IEF_PROF(cls, work, call)                 \
+  do {                                            \
+    if (g_nvtx) nvtxRangePushA(kClassNames[cls]); \
+    profiler().begin(cls, work, stream);          \
+    int _prc = (call);                            \
+    profiler().end(stream);                       \
+    if (g_nvtx) nvtxRangePop();                   \
+    if (_prc != 0) return _prc;                   \
   } while (0)
 
 int Model::init(int embed_dim, int num_heads, int layers, int refine_steps, float lambda, int noise_model, float nu,
@@ -264,6 +274,11 @@ int Model::forward(const void* img, const void* ev, int in_dtype, long long B, l
   IEF_TRY(check_loaded());
   IEF_CHECK(B >= 0 && T >= 0, "negative batch / length");
   if (B == 0 || T == 0) return IEFVAD_OK;
+  struct NvtxScope {
+    bool on;
+    explicit NvtxScope(bool o, const char* name) : on(o) { if (on) nvtxRangePushA(name); }
+    ~NvtxScope() { if (on) nvtxRangePop(); }
+  } nvtx_scope(g_nvtx, vr ? "iefvad forward (valid rows)" : "iefvad forward");
   IEF_CHECK(img && ev && fused && logits && image_mu && event_mu && image_logvar && event_logvar,
             "forward: null tensor pointer");
   IEF_CHECK((w_i == nullptr) == (w_e == nullptr), "forward: w_i and w_e are written together or not at all");

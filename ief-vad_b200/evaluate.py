@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import os
+
 import numpy as np
 import torch
 
@@ -41,6 +43,25 @@ def partition_videos(lengths: Sequence[int], world: int, maxlen: int = 256) -> L
     for p in parts:
         p.sort()
     return parts
+
+
+_NVTX = os.environ.get("IEFVAD_NVTX", "0") not in ("", "0")
+
+
+class _nvtx:
+    """NVTX range around a phase of an evaluation pass (IEFVAD_NVTX=1; the library marks the forward's stages itself)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def gather_layout(lengths: Sequence[int], parts: List[List[int]]):
@@ -210,6 +231,10 @@ class Evaluator:
     def gather(self, packed: torch.Tensor) -> torch.Tensor:
         """The single collective: all ranks' padded score vectors -> list-order score vector on every rank.  (Also used
         for the per-frame means of the fusion weights when `step(extras=...)` asks for them.)"""
+        with _nvtx("iefvad gather"):
+            return self._gather(packed)
+
+    def _gather(self, packed: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
             import torch.distributed as dist
             allv = torch.empty(self.world * max(self.max_count, 1), dtype=torch.float32, device=self.device)
@@ -224,6 +249,10 @@ class Evaluator:
     def metrics_async(self, scores: torch.Tensor) -> torch.Tensor:
         """AUC / AP overall, Ano-AUC and class-wise AUC / AP from one ranking pass; the [num_subsets, 4] table is
         copied to pinned host memory on the stream - nothing here waits for the device."""
+        with _nvtx("iefvad ranking"):
+            return self._metrics_async(scores)
+
+    def _metrics_async(self, scores: torch.Tensor) -> torch.Tensor:
         table = ops.auc_ap_multi(scores, self.pos, self.member, self.num_subsets, self.repeat)
         # a ring of pinned tables: a fresh pinned allocation per pass is a cudaHostAlloc whenever the previous ones are still
         # in flight (a loop of asynchronous passes), which serialises host and device
