@@ -5,10 +5,10 @@
 // the 16-bit result (pair) out).
 //
 // * The residual is added BY THE TENSOR CORE: after the 12 k-blocks of ctx . Wo^T the accumulator takes 4 (8 with a
-//   remainder part) more k-blocks  x[:, 64 tile columns] . I_64^T  into the 64 accumulator columns they belong to (N = 64
-//   MMAs with a 64 x 64 fp16 identity as the W operand) - exact (every product is x * 1 or x * 0, fp32 accumulation) and
-//   the tensor pipe has the time, while the CUDA cores, which bound the first version of this kernel, lose a
-//   shared-memory ring, two conversions and two additions per element.
+//   remainder part) more blocks  x[:, 64 tile columns] . I_64^T  into the 64 accumulator columns they belong to (N = 64
+//   MMAs with a 64 x 64 fp16 identity as the W operand, resident in shared memory; two x boxes share one ring stage) -
+//   exact (every product is x * 1 or x * 0, fp32 accumulation) and the tensor pipe has the time, while the CUDA cores,
+//   which bound the first version of this kernel, lose a shared-memory ring, two conversions and two additions per element.
 // * A LayerNorm row spans all 768 output columns but an accumulator tile is 256 columns wide (a CTA pair owns 256 rows x
 //   256 columns, cta_group::2, fp32 accumulators = half of TMEM, double-buffered).  So THREE pairs - a "group" - work on
 //   the three column tiles of the same 256-row block at the same time: they are ONE CLUSTER of 6 CTAs and exchange
@@ -111,7 +111,8 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
-  uint8_t* epi_base = smem + size_t(STAGES) * kStageBytes;
+  uint8_t* ident = smem + size_t(STAGES) * kStageBytes;              // this CTA's half (32 rows) of the 64 x 64 identity
+  uint8_t* epi_base = ident + kIBytes;
   float* prm = reinterpret_cast<float*>(epi_base + kEpiWarps * p.warp_bytes);      // [5][BN]
   PartConsts* pc = reinterpret_cast<PartConsts*>(reinterpret_cast<uint8_t*>(prm) + kParamBytes);
   constexpr int kRec = TWO ? 8 : 4;                                  // floats per (row, part) record: shift, S1, S2, A1 [, A2, A3, A4, -]
@@ -122,7 +123,8 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
   uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* xbar = tempty + 2;                                       // [2 teams][4 quarters]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 8);
+  uint64_t* ibar = xbar + 8;                                         // the identity halves of both CTAs have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ibar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,7 +133,8 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
   const uint32_t lead = crank & ~1u;                                 // the pair's leader CTA
   const int grp = blockIdx.x / kClusterCtas;
   const int n_blk = int(crank >> 1);
-  const int kKB = (p.dbg & 1) ? kKBMain : kKBMain + kKBRes * (1 + RES_LO);
+  constexpr int kResStages = kKBRes * (1 + RES_LO) / 2;              // two 64-column residual boxes per ring stage
+  const int kKB = (p.dbg & 1) ? kKBMain : kKBMain + kResStages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&ta);
@@ -148,6 +151,7 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
       mbar_init(&tempty[s], kEpiWarps);          // the 8 warps of the owning team in each CTA of the pair
     }
     for (int s = 0; s < 8; ++s) mbar_init(&xbar[s], 1);        // one local arrive.expect_tx per tile; the records arrive as tx bytes
+    mbar_init(ibar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -162,6 +166,11 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      {   // the identity, once: both CTAs' halves complete on the leader's barrier
+        const uint32_t lead_ibar = mapa_shared(smem_u32(ibar), lead);
+        if (rank == 0) mbar_arrive_expect_tx(ibar, 2 * kIBytes);
+        tma_load_2d_cg2(&tid, lead_ibar, ident, 0, int(rank) * (BK / 2));
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int mp = grp; mp < p.num_mp; mp += p.groups) {
@@ -170,7 +179,7 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + size_t(s) * kStageBytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), lead);
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], kb < kKBMain ? 2 * kStageBytes : 2 * (kABytes + kIBytes));
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kStageBytes);
           const int m_next = m_blk + 2 * p.groups;
           const bool pf = (p.dbg & 8) && mp + p.groups < p.num_mp;      // A/B knob: L2 prefetch of the next tile's A boxes (measured no gain)
           if (kb < kKBMain) {
@@ -178,13 +187,15 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
             tma_load_2d_cg2(&tw, lead_full, sa + kABytes, kb * BK, n_blk * BN + int(rank) * (BN / 2));
             if (pf) tma_prefetch_2d(&ta, kb * BK, m_next * BM);
           } else {
-            // residual block: A = x[rows, tile columns kk * 64 ..], W = this CTA's rows of the identity
-            const int kr = kb - kKBMain;
-            const int kk = kr & (kKBRes - 1);
-            const CUtensorMap* tr = (RES_LO && kr >= kKBRes) ? &trl : &trh;
-            tma_load_2d_cg2(tr, lead_full, sa, n_blk * BN + kk * BK, m_blk * BM);
-            tma_load_2d_cg2(&tid, lead_full, sa + kABytes, 0, int(rank) * (BK / 2));
-            if (pf) tma_prefetch_2d(tr, n_blk * BN + kk * BK, m_next * BM);
+            // residual stage: two A boxes x[rows, tile columns kk * 64 ..] (the W operand is the resident identity)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int kr = 2 * (kb - kKBMain) + b;
+              const int kk = kr & (kKBRes - 1);
+              const CUtensorMap* tr = (RES_LO && kr >= kKBRes) ? &trl : &trh;
+              tma_load_2d_cg2(tr, lead_full, sa + b * kABytes, n_blk * BN + kk * BK, m_blk * BM);
+              if (pf) tma_prefetch_2d(tr, n_blk * BN + kk * BK, m_next * BM);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -196,6 +207,7 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
       constexpr uint32_t idesc_res = make_idesc_f16(2 * BM, BK);
       const uint16_t pair_mask = uint16_t(3u << lead);
+      bool ident_ready = false;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -216,10 +228,21 @@ outproj_ln_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant_
             for (int k4 = 0; k4 < BK / 16; ++k4)
               umma_bf16_cg2(d_tmem, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
           } else {
-            const uint32_t d_res = d_tmem + uint32_t(((kb - kKBMain) & (kKBRes - 1)) * BK);     // the 64 columns this block adds to
+            if (!ident_ready) {
+              mbar_wait(ibar, 0);
+              tc_fence_after();
+              ident_ready = true;
+            }
+            const uint64_t di = make_smem_desc_sw128(smem_u32(ident));
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4)
-              umma_bf16_cg2(d_res, da + uint64_t(2 * k4), db + uint64_t(2 * k4), idesc_res, 1u);
+            for (int b = 0; b < 2; ++b) {
+              const int kr = 2 * (kb - kKBMain) + b;
+              const uint32_t d_res = d_tmem + uint32_t((kr & (kKBRes - 1)) * BK);     // the 64 columns this box adds to
+              const uint64_t dab = make_smem_desc_sw128(sa + uint32_t(b) * kABytes);
+#pragma unroll
+              for (int k4 = 0; k4 < BK / 16; ++k4)
+                umma_bf16_cg2(d_res, dab + uint64_t(2 * k4), di + uint64_t(2 * k4), idesc_res, 1u);
+            }
           }
           tc_commit_cg2(&empty[s], pair_mask);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -508,7 +531,7 @@ int outproj_ln(const OutprojLnArgs& a, int num_sms, cudaStream_t stream) {
   const int res_lo = a.res_lo ? 1 : 0, out_lo = a.out_lo ? 1 : 0, two = a.ln2_w ? 1 : 0;
   p.warp_bytes = kBox16 + (out_lo ? kBox16 : 0);
   const uint32_t xch_bytes = 2 * BM * kParts * (two ? 8 : 4) * 4;
-  const uint32_t fixed = 1024 + kEpiWarps * p.warp_bytes + kParamBytes + kConstBytes + xch_bytes + kBarBytes;
+  const uint32_t fixed = 1024 + kIBytes + kEpiWarps * p.warp_bytes + kParamBytes + kConstBytes + xch_bytes + kBarBytes;
   p.stages = int((kSmemLimit - fixed) / kStageBytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   static const int dbg = [] { const char* e = getenv("IEFVAD_OUTPROJ_LN_DBG"); return e ? atoi(e) : 0; }();

@@ -105,8 +105,13 @@ bce_kernel(const float* __restrict__ v, const float* __restrict__ labels, long l
 // LSD radix sort: 32-bit keys + 32-bit payload, 8 bits per pass, stable
 // =================================================================================================
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per CTA
+constexpr int RS_MAX_ITEMS = 16;                 // up to 4096 keys per CTA
+// keys per thread: as many as keep ~2 CTAs per SM busy (a real split is <= 150 k scores: with 4096-key tiles 19 CTAs did all
+// the work, and the scatter - 16 sequential rounds per CTA - took 25 us per pass), 16 for large inputs
+static int rs_items(long long n) {
+  long long it = n / (long long)(RS_THREADS) / 296;
+  return it < 1 ? 1 : (it > RS_MAX_ITEMS ? RS_MAX_ITEMS : int(it));
+}
 constexpr int RS_BINS = 256;
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -118,13 +123,12 @@ rs_init_kernel(const float* __restrict__ scores, long long n, uint32_t* __restri
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t* __restrict__ hist, int nblocks) {
+rs_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t* __restrict__ hist, int nblocks, int items) {
   __shared__ uint32_t h[RS_BINS];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const long long base = (long long)blockIdx.x * RS_TILE;
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
+  const long long base = (long long)blockIdx.x * (RS_THREADS * items);
+  for (int r = 0; r < items; ++r) {
     const long long i = base + r * RS_THREADS + threadIdx.x;
     if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xFF], 1u);
   }
@@ -166,7 +170,7 @@ rs_scan_bins_kernel(uint32_t* __restrict__ hist, int nblocks, uint32_t* __restri
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, long long n, int shift,
                   const uint32_t* __restrict__ hist, int nblocks, const uint32_t* __restrict__ totals,
-                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int items) {
   __shared__ uint32_t bin_base[RS_BINS];                  // global offset of this tile's first key of each bin
   __shared__ uint32_t running[RS_BINS];                   // keys of each bin already placed by earlier rounds
   __shared__ uint32_t warp_cnt[RS_THREADS / 32][RS_BINS];
@@ -190,8 +194,8 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
   }
   for (int w = 0; w < RS_THREADS / 32; ++w) warp_cnt[w][threadIdx.x] = 0;
   __syncthreads();
-  const long long base = (long long)blockIdx.x * RS_TILE;
-  for (int r = 0; r < RS_ITEMS; ++r) {
+  const long long base = (long long)blockIdx.x * (RS_THREADS * items);
+  for (int r = 0; r < items; ++r) {
     const long long i = base + r * RS_THREADS + threadIdx.x;
     const bool valid = i < n;
     uint32_t key = 0, val = 0, digit = 0;
@@ -427,13 +431,14 @@ struct Tmp {
 // sorts (keys, vals) ascending by key, stable; result ends in (keys_a, vals_a)
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, long long n,
                      uint32_t* hist, uint32_t* totals, cudaStream_t st) {
-  const int nblocks = int((n + RS_TILE - 1) / RS_TILE);
+  const int items = rs_items(n);
+  const int nblocks = int((n + RS_THREADS * items - 1) / (RS_THREADS * items));
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = pass * 8;
-    rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, n, shift, hist, nblocks);
+    rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, n, shift, hist, nblocks, items);
     rs_scan_bins_kernel<<<RS_BINS, RS_THREADS, 0, st>>>(hist, nblocks, totals);
-    rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, n, shift, hist, nblocks, totals, ko, vo);
+    rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, n, shift, hist, nblocks, totals, ko, vo, items);
     count_launches(3);
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
@@ -490,7 +495,7 @@ int sort_scores(const float* scores, long long n, int* order, uint32_t* keys_sor
   IEF_CHECK(scores && order, "sort_scores: null argument");
   if (n == 0) return IEFVAD_OK;
   Tmp tmp(st);
-  const int nblocks = int((n + RS_TILE - 1) / RS_TILE);
+  const int nblocks = int((n + RS_THREADS * rs_items(n) - 1) / (RS_THREADS * rs_items(n)));
   uint32_t *ka, *kb, *vb, *hist, *totals;
   IEF_TRY(tmp.get(&ka, n));
   IEF_TRY(tmp.get(&kb, n));
@@ -520,7 +525,7 @@ int auc_ap_multi(const float* scores, const int* pos, const uint32_t* member, lo
     IEF_CUDA(cudaStreamSynchronize(st));
     return IEFVAD_OK;
   }
-  const int nblocks = int((n + RS_TILE - 1) / RS_TILE);
+  const int nblocks = int((n + RS_THREADS * rs_items(n) - 1) / (RS_THREADS * rs_items(n)));
   const int ntiles = int((n + SC_TILE - 1) / SC_TILE);
   uint32_t *ka, *kb, *va, *vb, *hist, *totals;
   Tri *tile_sums, *grand;
