@@ -77,6 +77,7 @@ struct TcMaps {
   CUtensorMap r2;
   CUtensorMap o0, o1;           // fp32 outputs (columns below / from split_col)
   CUtensorMap h, l;             // bf16 hi / lo outputs; in EPI_QKV: q / k as 4-D {d, t, head, batch}
+  CUtensorMap v;                // EPI_QKV: V^T as 3-D {t, head * dh + d, batch}
 };
 
 template <int BN, int CG = 1>
@@ -309,6 +310,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
         const long long row = (long long)row0 + lane;
         const long long b = row / ep.T;
         const int t = int(row - b * ep.T);
+        if (which == 2 && ep.qk_tma) {
+          // V^T [B, H, dh, Tpad] through a transposed box: lane = t writes its 32 d values down a column (each instruction
+          // fills one 64-byte box row, conflict-free), then ONE TMA store instead of 32 scattered 2-byte stores per thread
+          uint8_t* hb = Hb + size_t(n_out & 1) * kBfBox;
+          __syncwarp();                                  // lane 0 is back from bulk_wait_read: box [n_out & 1] is free
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (ep.hi_fp16) *reinterpret_cast<__half*>(hb + j * 64 + lane * 2) = __float2half_rn(v[j]);
+            else *reinterpret_cast<bf16*>(hb + j * 64 + lane * 2) = __float2bfloat16_rn(v[j]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const long long b0 = (long long)row0 / ep.T;   // T % 32 == 0: all 32 rows share the batch element
+            tma_store_3d(&tm.v, hb, int(row0 - b0 * ep.T), h * ep.dh + d0, int(b0));
+            finish_chunk();
+          }
+          ++n_out;
+          return;
+        }
         if (which == 2) {
           // V^T [B, H, dh, Tpad]: consecutive lanes = consecutive t, so each of the 32 stores is one 64-byte run
           if (row < M) {
@@ -604,6 +625,8 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
     const uint32_t box[4] = {CW, 32, 1, 1};
     IEF_TRY(make_tmap_4d(&tm.h, ep.q, dims, strides, box, TM_BF16, TM_SWIZZLE_64B));
     IEF_TRY(make_tmap_4d(&tm.l, ep.k, dims, strides, box, TM_BF16, TM_SWIZZLE_64B));
+    IEF_TRY(make_tmap_3d(&tm.v, ep.vt, uint64_t(ep.Tpad), uint64_t(ep.H) * ep.dh, Bn, uint64_t(ep.Tpad) * 2,
+                         uint64_t(ep.H) * ep.dh * ep.Tpad * 2, CW, 32, 1, TM_SWIZZLE_NONE));
   }
   const int num_m = (g.M + BM * CG - 1) / (BM * CG), num_n = (g.N + BN - 1) / BN;
   const int tiles = num_m * num_n;                       // one per CTA (CG == 1) or per CTA pair (CG == 2)
