@@ -150,3 +150,76 @@ def test_module_layernorm_and_quickgelu_standalone():
     assert torch.allclose(got32.cpu(), ref, atol=1e-5)
     q = QuickGELU()(x.cuda())
     assert torch.allclose(q.cpu(), x * torch.sigmoid(1.702 * x), atol=1e-6)
+
+
+# ------------------------------------------------------------------ rows D1-D3 at the config-5 size (T = 16 384)
+# The full-size outputs (1 GiB adjacency matrices) are compared with float64 restatements of the reference's lines on
+# SAMPLED rows: every row of these operators depends on all T positions, so a sampled row exercises the whole reduction.
+T5 = 16384
+
+
+def _sample_rows(n=48, seed=5):
+    rng = np.random.default_rng(seed)
+    return np.unique(np.concatenate([[0, 1, T5 // 2 - 1, T5 // 2, T5 - 2, T5 - 1], rng.integers(0, T5, n)]))
+
+
+def test_distance_adj_c5_size(mods):
+    layers, _ = mods
+    got = layers.DistanceAdj().cuda()(1, T5)
+    rows = _sample_rows()
+    idx = np.arange(T5)
+    ref = np.exp(-np.abs(rows[:, None] - idx[None, :]).astype(np.float32) / np.exp(np.float32(1.0)))   # layers.py:172-179
+    np.testing.assert_allclose(got[0, torch.from_numpy(rows).cuda()].cpu().numpy(), ref, rtol=3e-5, atol=1e-37)
+
+
+def test_distance_scan_c5_size(mods):
+    layers, _ = mods
+    s = np.random.default_rng(7).standard_normal((1, T5, 768)).astype(np.float32)
+    got = layers.distance_scan(_c(s)).cpu().numpy()
+    ref = O.graph_convolution_distance_scan(s.astype(np.float64), np.eye(768))
+    assert O.max_norm_err(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize("plan", ["fp32", "split"])
+def test_similarity_adj_c5_size(mods, plan):
+    layers, _ = mods
+    rng = np.random.default_rng(11)
+    Din = Dout = 128
+    # clustered rows: members of a cluster are above the 0.7 cosine threshold, different clusters far below it
+    centres = rng.standard_normal((64, Din))
+    lab = rng.integers(0, 64, T5)
+    x = (centres[lab] + 0.25 * rng.standard_normal((T5, Din))).astype(np.float32)[None]
+    m = layers.SimilarityAdj(Din, Dout).cuda()
+    m.precision = plan
+    got = m(_c(x), None)
+    rows = _sample_rows(24)
+    w0 = m.weight0.detach().cpu().numpy().astype(np.float64)
+    theta = x[0].astype(np.float64) @ w0                                     # layers.py:132-140
+    nrm = np.sqrt((theta * theta).sum(-1))
+    cos = (theta[rows] @ theta.T) / (nrm[rows, None] * nrm[None, :] + 1e-20)
+    margin = {"fp32": 1e-5, "split": 1e-4}[plan]
+    safe = ~(np.abs(cos - 0.7) < margin).any(axis=1)                         # no entry within rounding of the threshold
+    assert safe.sum() >= 8
+    t = np.where(cos > 0.7, cos, 0.0)
+    ref = np.exp(t - t.max(axis=1, keepdims=True))
+    ref /= ref.sum(axis=1, keepdims=True)
+    g = got[0, torch.from_numpy(rows).cuda()].cpu().numpy()
+    assert np.abs(g[safe] - ref[safe]).max() / np.abs(ref[safe]).max() < TOL[plan]
+
+
+@pytest.mark.parametrize("plan", ["fp32", "split"])
+def test_graph_convolution_c5_size(mods, plan):
+    layers, _ = mods
+    torch.manual_seed(13)
+    D = 128
+    gc = layers.GraphConvolution(D, D, bias=True, residual=True).cuda()
+    gc.precision = plan
+    x = torch.randn(1, T5, D, device="cuda")
+    adj = layers.DistanceAdj().cuda()(1, T5)                                 # the adjacency model/layers.py pairs it with
+    got = gc(x, adj)
+    rows = _sample_rows(32)
+    r = torch.from_numpy(rows).cuda()
+    support = x[0].double() @ gc.weight.detach().double()                    # layers.py:101-110
+    ref = adj[0, r].double() @ support + gc.bias.detach().double() + x[0, r].double()
+    err = (got[0, r].double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < TOL[plan], err
