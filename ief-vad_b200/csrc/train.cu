@@ -12,6 +12,7 @@
 //   clas2_bwd                               backward of the MIL top-k BCE loss (train/loss.py:18-30)
 //   transpose, colsum, relu_bwd, axpy, outer
 #include "common.cuh"
+#include "philox.cuh"
 #include "train.cuh"
 
 namespace iefvad {
@@ -26,27 +27,6 @@ __host__ int grid_for(long long work_items, int num_sms, int per_sm = 8) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
-}
-
-// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al., SC'11)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-// keep (1) / drop (0) decision of attention weight (bh, query i, key j): one Philox call serves 4 consecutive keys
-__device__ __forceinline__ float keep_scale(unsigned long long seed, int bh, int i, int j, uint32_t thresh, float inv_keep) {
-  const uint4 r = philox4x32_10(make_uint4(uint32_t(j >> 2), uint32_t(i), uint32_t(bh), 0u),
-                                make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
-  const uint32_t v = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
-  return v >= thresh ? inv_keep : 0.f;           // P(drop) = thresh / 2^32
 }
 
 // ---------------------------------------------------------------- attention, training form (fp32, one warp per 4 rows)
@@ -479,6 +459,7 @@ int attn_train_fwd(const float* qkv, int B, int T, int H, int dh, float p_drop, 
   const uint32_t thr = p_drop > 0.f ? uint32_t(double(p_drop) * 4294967296.0) : 0u;
   const float ik = 1.f / (1.f - p_drop);
   if (B == 0 || T == 0) return IEFVAD_OK;
+  if (attn_train_mma_supported(dh)) return attn_train_fwd_mma(qkv, B, T, H, dh, qs, thr, ik, seed, out, lse, stream);
   switch (dh) {
     case 32: attn_train_fwd_kernel<32><<<grid, 128, 0, stream>>>(qkv, out, lse, T, H, D, qs, thr, ik, seed); break;
     case 64: attn_train_fwd_kernel<64><<<grid, 128, 0, stream>>>(qkv, out, lse, T, H, D, qs, thr, ik, seed); break;
@@ -500,6 +481,10 @@ int attn_train_bwd(const float* qkv, const float* out, const float* dout, const 
   const uint32_t thr = p_drop > 0.f ? uint32_t(double(p_drop) * 4294967296.0) : 0u;
   const float ik = 1.f / (1.f - p_drop);
   attn_delta_kernel<<<grid_for((long long)B * H * T * 32, num_sms), kThreads, 0, stream>>>(out, dout, delta_scratch, B, T, H, dh);
+  if (attn_train_mma_supported(dh)) {
+    count_launches(1);
+    return attn_train_bwd_mma(qkv, dout, lse, delta_scratch, B, T, H, dh, qs, thr, ik, seed, dqkv, stream);
+  }
 #define IEF_BWD(DH_)                                                                                                          \
   attn_train_bwd_q_kernel<DH_><<<grid, 128, 0, stream>>>(qkv, dout, lse, delta_scratch, dqkv, T, H, D, qs, thr, ik, seed);     \
   attn_train_bwd_kv_kernel<DH_><<<grid, 128, 0, stream>>>(qkv, dout, lse, delta_scratch, dqkv, T, H, D, qs, thr, ik, seed);

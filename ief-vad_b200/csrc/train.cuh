@@ -12,6 +12,13 @@ int attn_train_fwd(const float* qkv, int B, int T, int H, int dh, float p_drop, 
 int attn_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int B, int T, int H, int dh,
                    float p_drop, unsigned long long seed, float* delta_scratch, float* dqkv, int num_sms, cudaStream_t stream);
 
+// the same on the tensor cores (mma.sync TF32, train_attn_mma.cu); qs = 1 / sqrt(dh), thr = p_drop * 2^32, ik = 1 / (1 - p_drop)
+bool attn_train_mma_supported(int dh);
+int attn_train_fwd_mma(const float* qkv, int B, int T, int H, int dh, float qs, uint32_t thr, float ik, unsigned long long seed,
+                       float* out, float* lse, cudaStream_t stream);
+int attn_train_bwd_mma(const float* qkv, const float* dout, const float* lse, const float* delta, int B, int T, int H, int dh,
+                       float qs, uint32_t thr, float ik, unsigned long long seed, float* dqkv, cudaStream_t stream);
+
 int train_colsum_blocks(long long rows, int num_sms);
 // scratch: 2 * rows + 2 * train_colsum_blocks(rows) * D floats
 int layernorm_bwd(const float* x, const float* gamma, const float* dy, long long rows, int D, float eps, float* dx, float* dgamma,
