@@ -431,6 +431,23 @@ int iefvad_linear(const float* x, const float* w, const float* bias, const float
   g.fp16 = plan == 2 ? 1 : 0;
   g.force_bn = tile_n == 512 ? 256 : tile_n;          // 512 = 256-column tiles on CTA pairs
   g.force_cg = tile_n == 512 ? 2 : (tile_n ? 1 : 0);
+  // Small output, long contraction (the wgrad GEMMs of the training step: [768, 768] = dY^T [768, 16 384] . X^T): without
+  // split-K 72 CTAs walk 768 k-blocks each.  K slices become extra row tiles of a [S x rows, out_f] partial buffer (256-column
+  // tiles on CTA pairs), summed in slice order afterwards - deterministic, unlike atomics.
+  if (tile_n == 0 && !bias && !resid && act == ACT_NONE && rows % 256 == 0 && out_f % 256 == 0 && in_f >= 4096 &&
+      (rows / 256) * (out_f / 256) * 2 <= sms / 2) {
+    int S = (sms / 2) / int((rows / 256) * (out_f / 256));
+    while (S > 1 && (in_f / 64) % S != 0) --S;
+    if (S > 1) {
+      void* part;
+      IEF_TRY(sc.get(&part, size_t(S) * rows * out_f * 4));
+      ep.alpha = 1.f;
+      ep.out_f32 = static_cast<float*>(part);
+      g.ksplit = S; g.force_bn = 256; g.force_cg = 2;
+      IEF_TRY(gemm_tc(g, ep, sms, st));
+      return sum_slices(static_cast<const float*>(part), S, rows * out_f, alpha, out, sms, st);
+    }
+  }
   return gemm_tc(g, ep, sms, st);
 }
 

@@ -380,6 +380,19 @@ classifier_kernel(const float* __restrict__ x, long long M, int D, const float* 
   }
 }
 
+// out[i] = alpha * sum_s part[s * n + i], slices added in index order (split-K reduction: run-to-run deterministic)
+__global__ void __launch_bounds__(kThreads)
+sum_slices_kernel(const float4* __restrict__ part, int S, long long n4, float alpha, float4* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = part[i];
+    for (int s = 1; s < S; ++s) {
+      const float4 b = part[(long long)s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[i] = make_float4(alpha * a.x, alpha * a.y, alpha * a.z, alpha * a.w);
+  }
+}
+
 }  // namespace
 
 int ingest(const void* in, int dtype, long long n, float* out_f32, bf16* out_hi, bf16* out_lo, int num_sms,
@@ -540,6 +553,16 @@ int classifier(const float* x, long long M, int D, const float* w, const float* 
   IEF_CHECK(D % 4 == 0, "classifier: D=%d must be a multiple of 4", D);
   if (M == 0) return IEFVAD_OK;
   classifier_kernel<<<grid_for(M * 32, num_sms), kThreads, 0, stream>>>(x, M, D, w, bias, logits, scores, nonfinite);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int sum_slices(const float* part, int S, long long n, float alpha, float* out, int num_sms, cudaStream_t stream) {
+  IEF_CHECK(n % 4 == 0 && S >= 1, "sum_slices: element count %lld must be a multiple of 4", n);
+  if (n == 0) return IEFVAD_OK;
+  sum_slices_kernel<<<grid_for(n / 4, num_sms), kThreads, 0, stream>>>(reinterpret_cast<const float4*>(part), S, n / 4, alpha,
+                                                                       reinterpret_cast<float4*>(out));
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

@@ -54,6 +54,9 @@ int fuse_rows(const float* mu_i, const float* mu_e, const float* lv_i, const flo
 int gather_rows(const bf16* ctx, const float* x, const int* rowmap, long long row_base, long long n_rows, int D,
                 bf16* ctx_c, float* x_c, int num_sms, cudaStream_t stream);
 
+// out[i] = alpha * sum_s part[s * n + i] (slices in index order): the reduction of a split-K GEMM
+int sum_slices(const float* part, int S, long long n, float alpha, float* out, int num_sms, cudaStream_t stream);
+
 // fp32 -> fp16 (weights of the fp16-operand refinement GEMMs)
 int to_half(const float* in, long long n, void* out_f16, int num_sms, cudaStream_t stream);
 

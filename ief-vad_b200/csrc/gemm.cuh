@@ -16,6 +16,8 @@ struct GemmTcArgs {
   int fp16 = 0;                // A_hi / W_hi hold fp16 (E5M10) instead of bf16: 8x finer operand rounding, same MMA rate
   int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256 (tests, tuning)
   int force_stages = 0;        // 0 = as many smem stages as fit beside the epilogue buffers (tuning)
+  int ksplit = 1;              // split-K (small M x N, long K: the wgrad GEMMs): slice s accumulates into rows [s M, (s + 1) M) of
+                               // out_f32, which must hold ksplit x M rows; the caller sums the slices (fixed order)
   int force_cg = 0;            // 0 = heuristic, 1 = one CTA per tile, 2 = CTA pair (cta_group::2, 256-row tiles)
 };
 

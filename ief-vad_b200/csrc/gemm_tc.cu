@@ -69,6 +69,7 @@ struct TcEpi {
   int T = 0, H = 0, dh = 0, dhp = 0, Tpad = 0, D = 0;
   float qscale = 1.f;
   int qk_tma = 0;          // q / k leave through 4-D TMA stores (T % 32 == 0), else per-thread 16-byte stores
+  int ksplit = 1;          // split-K: slice s of the K range accumulates into rows [s * M, (s + 1) * M) of the output
 };
 
 struct TcMaps {
@@ -125,9 +126,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // rank in the CTA pair; 0 = leader
   const int num_m = (M + BM * CG - 1) / (BM * CG);               // tiles of BM * CG rows (one per CTA / pair)
   const int num_n = (N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles = num_m * num_n * ep.ksplit;               // split-K: the output has ksplit row slices of M rows each
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
-  const int kb_per_seg = K / BK;
+  const int kb_per_seg = K / BK / ep.ksplit;                      // k-blocks a tile walks per operand pair
   const int total_kb = kb_per_seg * nsplit;
 
   if (warp == 0 && lane == 0) {
@@ -168,9 +169,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps tm, int M, int N, int K, int nspli
       int s = 0;
       uint32_t ph = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = (tile / num_n) * CG + int(rank), n_blk = tile % num_n;
+        const int m_out = (tile / num_n) * CG + int(rank), n_blk = tile % num_n;
+        const int m_blk = m_out % (num_m * CG);                    // operand row block; m_out / (num_m * CG) = the K slice
+        const int k_first = (m_out / (num_m * CG)) * kb_per_seg;
         for (int kb = 0; kb < total_kb; ++kb) {
-          const int seg = kb / kb_per_seg, kk = kb - seg * kb_per_seg;
+          const int seg = kb / kb_per_seg, kk = k_first + kb - seg * kb_per_seg;
           const CUtensorMap* ma = (seg == 2) ? &tm.a1 : &tm.a0;   // hi.hi, hi.lo, lo.hi
           const CUtensorMap* mb = (seg == 1) ? &tm.b1 : &tm.b0;
           mbar_wait(&empty[s], ph ^ 1);
@@ -548,6 +551,13 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
   e.mode = ep.mode; e.bias = ep.bias; e.act = ep.act; e.alpha = ep.alpha; e.split_col = ep.split_col;
   e.idesc = g.fp16 ? make_idesc_f16(BM * CG, BN) : make_idesc_bf16(BM * CG, BN);
   e.hi_fp16 = ep.hi_fp16;
+  e.ksplit = g.ksplit > 1 ? g.ksplit : 1;
+  if (e.ksplit > 1) {
+    IEF_CHECK(ep.mode == EPI_ROWMAJOR && !ep.bias && !ep.resid && !ep.resid_h16 && ep.act == ACT_NONE && ep.out_f32 && !ep.out_hi &&
+              ep.split_col >= g.N, "gemm_tc: split-K writes plain fp32 partial sums (no bias / residual / activation)");
+    IEF_CHECK(g.M % (BM * CG) == 0 && (g.K / BK) % e.ksplit == 0, "gemm_tc: split-K needs M %% %d == 0 and K / %d divisible by %d",
+              BM * CG, BK, e.ksplit);
+  }
   IEF_CHECK(!g.fp16 || g.nsplit == 1, "gemm_tc: fp16 operands are single-pass (nsplit == 1)");
   const bool r16 = ep.resid_h16 != nullptr;
   IEF_CHECK(!r16 || (ep.resid == nullptr && ep.mode == EPI_ROWMAJOR && ep.act == ACT_NONE),
@@ -606,7 +616,7 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
     IEF_TRY(make_tmap_2d(&tm.r, ep.resid, g.N, g.M, uint64_t(ep.ld_resid) * 4, CW, 32, TM_F32, TM_SWIZZLE_128B));
   if (e.has_f32) {
     const uint64_t w0 = ep.split_col < g.N ? ep.split_col : g.N;
-    IEF_TRY(make_tmap_2d(&tm.o0, ep.out_f32, w0, g.M, uint64_t(ep.ld_f32) * 4, CW, 32, TM_F32, TM_SWIZZLE_128B));
+    IEF_TRY(make_tmap_2d(&tm.o0, ep.out_f32, w0, uint64_t(g.M) * e.ksplit, uint64_t(ep.ld_f32) * 4, CW, 32, TM_F32, TM_SWIZZLE_128B));
     if (ep.split_col < g.N) {
       IEF_CHECK(ep.out_f32_b != nullptr, "gemm_tc: split_col set without out_f32_b");
       IEF_TRY(make_tmap_2d(&tm.o1, ep.out_f32_b, g.N - ep.split_col, g.M, uint64_t(ep.ld_f32) * 4, CW, 32, TM_F32,
@@ -629,7 +639,7 @@ int launch_bn(const GemmTcArgs& g, const EpiParams& ep, int num_sms, cudaStream_
                          uint64_t(ep.H) * ep.dh * ep.Tpad * 2, CW, 32, 1, TM_SWIZZLE_NONE));
   }
   const int num_m = (g.M + BM * CG - 1) / (BM * CG), num_n = (g.N + BN - 1) / BN;
-  const int tiles = num_m * num_n;                       // one per CTA (CG == 1) or per CTA pair (CG == 2)
+  const int tiles = num_m * num_n * e.ksplit;            // one per CTA (CG == 1) or per CTA pair (CG == 2)
   const int max_groups = num_sms / CG;
   const int grid = (tiles < max_groups ? tiles : max_groups) * CG;
   if (ep.mode == EPI_QKV) {

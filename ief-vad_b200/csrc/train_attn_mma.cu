@@ -56,6 +56,22 @@ __device__ __forceinline__ void load_tile(uint32_t* dst, const float* src, long 
   }
 }
 
+// the same through cp.async (16-byte pieces, zero-filled past `limit`): the next block's tiles travel while this one computes
+template <int DH>
+__device__ __forceinline__ void load_tile_async(uint32_t* dst, const float* src, long long row_stride, int r0, int nrows, int limit) {
+  constexpr int P = DH + 4, C4 = DH / 4;
+  for (int i = threadIdx.x; i < nrows * C4; i += kThreads) {
+    const int r = i / C4, c = i - r * C4;
+    const int t = r0 + r;
+    const float* g = src + (long long)(t < limit ? t : 0) * row_stride + c * 4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + r * P + c * 4)), "l"(g), "r"(t < limit ? 16 : 0)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // fp32 word -> (hi, lo) TF32 pair
 __device__ __forceinline__ void split_tf32(uint32_t w, uint32_t& hi, uint32_t& lo) {
   const float x = __uint_as_float(w);
@@ -121,22 +137,33 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, floa
   constexpr int P = DH + 4;
   extern __shared__ uint32_t sm[];
   uint32_t* Qs = sm;                 // [BQ][P]
-  uint32_t* Ks = Qs + BQ * P;        // [BC][P]
-  uint32_t* Vs = Ks + BC * P;        // [BC][P]
+  uint32_t* KV = Qs + BQ * P;        // [2 buffers][K: BC x P | V: BC x P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z, bh = b * H + h;
   const int q0 = blockIdx.x * BQ;
   const float* base = qkv + (long long)b * T * 3 * D + h * DH;
+  load_tile_async<DH>(KV, base + D, 3 * D, 0, BC, T);
+  load_tile_async<DH>(KV + BC * P, base + 2 * D, 3 * D, 0, BC, T);
+  cp_async_commit();
   load_tile<DH>(Qs, base, 3 * D, q0, BQ, T, qscale);
   float o[DH / 8][4];
 #pragma unroll
   for (int nd = 0; nd < DH / 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
   float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
   const int rq[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
-  for (int k0 = 0; k0 < T; k0 += BC) {
-    __syncthreads();
-    load_tile<DH>(Ks, base + D, 3 * D, k0, BC, T, 1.f);
-    load_tile<DH>(Vs, base + 2 * D, 3 * D, k0, BC, T, 1.f);
+  int buf = 0;
+  for (int k0 = 0; k0 < T; k0 += BC, buf ^= 1) {
+    const uint32_t* Ks = KV + buf * 2 * BC * P;
+    const uint32_t* Vs = Ks + BC * P;
+    if (k0 + BC < T) {
+      uint32_t* nx = KV + (buf ^ 1) * 2 * BC * P;
+      load_tile_async<DH>(nx, base + D, 3 * D, k0 + BC, BC, T);
+      load_tile_async<DH>(nx + BC * P, base + 2 * D, 3 * D, k0 + BC, BC, T);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[4][4];
 #pragma unroll
@@ -181,6 +208,7 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, floa
       o[nd][0] *= alpha[0]; o[nd][1] *= alpha[0]; o[nd][2] *= alpha[1]; o[nd][3] *= alpha[1];
     }
     mma_cols<DH>(o, s, Vs, g, t);
+    __syncthreads();                 // everyone is done with this buffer before the next iteration's prefetch overwrites it
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -209,12 +237,14 @@ attn_bwd_q_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d
   extern __shared__ uint32_t sm[];
   uint32_t* Qs = sm;                 // [BQ][P] scaled queries
   uint32_t* Gs = Qs + BQ * P;        // [BQ][P] dout rows
-  uint32_t* Ks = Gs + BQ * P;        // [BC][P]
-  uint32_t* Vs = Ks + BC * P;        // [BC][P]
+  uint32_t* KV = Gs + BQ * P;        // [2 buffers][K: BC x P | V: BC x P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z, bh = b * H + h;
   const int q0 = blockIdx.x * BQ;
   const float* base = qkv + (long long)b * T * 3 * D + h * DH;
+  load_tile_async<DH>(KV, base + D, 3 * D, 0, BC, T);
+  load_tile_async<DH>(KV + BC * P, base + 2 * D, 3 * D, 0, BC, T);
+  cp_async_commit();
   load_tile<DH>(Qs, base, 3 * D, q0, BQ, T, qscale);
   load_tile<DH>(Gs, dout + (long long)b * T * D + h * DH, D, q0, BQ, T, 1.f);
   float dq[DH / 8][4];
@@ -227,10 +257,19 @@ attn_bwd_q_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d
     L[r] = rq[r] < T ? lse[(long long)bh * T + rq[r]] : 0.f;
     Dl[r] = rq[r] < T ? delta[(long long)bh * T + rq[r]] : 0.f;
   }
-  for (int k0 = 0; k0 < T; k0 += BC) {
-    __syncthreads();
-    load_tile<DH>(Ks, base + D, 3 * D, k0, BC, T, 1.f);
-    load_tile<DH>(Vs, base + 2 * D, 3 * D, k0, BC, T, 1.f);
+  int buf = 0;
+  for (int k0 = 0; k0 < T; k0 += BC, buf ^= 1) {
+    const uint32_t* Ks = KV + buf * 2 * BC * P;
+    const uint32_t* Vs = Ks + BC * P;
+    if (k0 + BC < T) {
+      uint32_t* nx = KV + (buf ^ 1) * 2 * BC * P;
+      load_tile_async<DH>(nx, base + D, 3 * D, k0 + BC, BC, T);
+      load_tile_async<DH>(nx + BC * P, base + 2 * D, 3 * D, k0 + BC, BC, T);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[4][4], dp[4][4];
 #pragma unroll
@@ -257,6 +296,7 @@ attn_bwd_q_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d
       }
     }
     mma_cols<DH>(dq, s, Ks, g, t);
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -278,14 +318,24 @@ attn_bwd_kv_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   extern __shared__ uint32_t sm[];
   uint32_t* Ks = sm;                 // [BQ][P] this CTA's keys
   uint32_t* Vs = Ks + BQ * P;        // [BQ][P]
-  uint32_t* Qs = Vs + BQ * P;        // [BC][P] scaled queries of the block
-  uint32_t* Gs = Qs + BC * P;        // [BC][P] dout rows of the block
-  float* Ls = reinterpret_cast<float*>(Gs + BC * P);   // [BC]
-  float* Ds = Ls + BC;                                  // [BC]
+  uint32_t* QG = Vs + BQ * P;        // [2 buffers][Q: BC x P (unscaled) | dout: BC x P] of the streamed query block
+  float* LD = reinterpret_cast<float*>(QG + 4 * BC * P);   // [2 buffers][lse: BC | delta: BC]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z, bh = b * H + h;
   const int kbase = blockIdx.x * BQ;
   const float* base = qkv + (long long)b * T * 3 * D + h * DH;
+  const float* gbase = dout + (long long)b * T * D + h * DH;
+  auto prefetch = [&](int q0, int bf) {
+    load_tile_async<DH>(QG + bf * 2 * BC * P, base, 3 * D, q0, BC, T);
+    load_tile_async<DH>(QG + bf * 2 * BC * P + BC * P, gbase, D, q0, BC, T);
+    cp_async_commit();
+    if (threadIdx.x < BC) {
+      const int tq = q0 + threadIdx.x;
+      LD[bf * 2 * BC + threadIdx.x] = tq < T ? lse[(long long)bh * T + tq] : 0.f;
+      LD[bf * 2 * BC + BC + threadIdx.x] = tq < T ? delta[(long long)bh * T + tq] : 0.f;
+    }
+  };
+  prefetch(0, 0);
   load_tile<DH>(Ks, base + D, 3 * D, kbase, BQ, T, 1.f);
   load_tile<DH>(Vs, base + 2 * D, 3 * D, kbase, BQ, T, 1.f);
   float dk[DH / 8][4], dv[DH / 8][4];
@@ -294,14 +344,17 @@ attn_bwd_kv_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ 
 #pragma unroll
     for (int e = 0; e < 4; ++e) dk[nd][e] = dv[nd][e] = 0.f;
   const int rk[2] = {kbase + warp * 16 + g, kbase + warp * 16 + g + 8};
-  for (int q0 = 0; q0 < T; q0 += BC) {
-    __syncthreads();
-    load_tile<DH>(Qs, base, 3 * D, q0, BC, T, qscale);
-    load_tile<DH>(Gs, dout + (long long)b * T * D + h * DH, D, q0, BC, T, 1.f);
-    if (threadIdx.x < BC) {
-      const int tq = q0 + threadIdx.x;
-      Ls[threadIdx.x] = tq < T ? lse[(long long)bh * T + tq] : 0.f;
-      Ds[threadIdx.x] = tq < T ? delta[(long long)bh * T + tq] : 0.f;
+  int buf = 0;
+  for (int q0 = 0; q0 < T; q0 += BC, buf ^= 1) {
+    const uint32_t* Qs = QG + buf * 2 * BC * P;
+    const uint32_t* Gs = Qs + BC * P;
+    const float* Ls = LD + buf * 2 * BC;
+    const float* Ds = Ls + BC;
+    if (q0 + BC < T) {
+      prefetch(q0 + BC, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     // transposed tiles: rows = this warp's keys, columns = the block's queries
@@ -318,13 +371,14 @@ attn_bwd_kv_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ 
       for (int e = 0; e < 4; ++e) {
         const int qc = nt * 8 + 2 * t + (e & 1), tq = q0 + qc, key = rk[e >> 1];
         const bool valid = tq < T && key < T;
-        const float p = valid ? expf(st[nt][e] - Ls[qc]) : 0.f;
+        const float p = valid ? expf(st[nt][e] * qscale - Ls[qc]) : 0.f;      // the streamed queries are unscaled
         const float ks = (drop_thresh && valid) ? keep_scale(seed, bh, tq, key, drop_thresh, inv_keep) : 1.f;
         st[nt][e] = p * ks;                                   // dropped weights P~^T
         dpt[nt][e] = p * (dpt[nt][e] * ks - Ds[qc]);          // dS^T
       }
     mma_cols<DH>(dv, st, Gs, g, t);
-    mma_cols<DH>(dk, dpt, Qs, g, t);                          // Qs holds q * scale: d s / d k = scale * q
+    mma_cols<DH>(dk, dpt, Qs, g, t);                          // d s / d k = scale * q: the scale is applied to the sum below
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -332,7 +386,7 @@ attn_bwd_kv_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ 
     float* dst = dqkv + ((long long)b * T + rk[r]) * 3 * D + h * DH;
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd) {
-      *reinterpret_cast<float2*>(dst + D + nd * 8 + 2 * t) = make_float2(dk[nd][2 * r], dk[nd][2 * r + 1]);
+      *reinterpret_cast<float2*>(dst + D + nd * 8 + 2 * t) = make_float2(dk[nd][2 * r] * qscale, dk[nd][2 * r + 1] * qscale);
       *reinterpret_cast<float2*>(dst + 2 * D + nd * 8 + 2 * t) = make_float2(dv[nd][2 * r], dv[nd][2 * r + 1]);
     }
   }
@@ -356,7 +410,7 @@ int attn_train_fwd_mma(const float* qkv, int B, int T, int H, int dh, float qs, 
   const dim3 grid((T + BQ - 1) / BQ, H, B);
 #define IEF_FWD(DH_)                                                                                                  \
   {                                                                                                                    \
-    const size_t smem = size_t(BQ + 2 * BC) * (DH_ + 4) * 4;                                                           \
+    const size_t smem = size_t(BQ + 4 * BC) * (DH_ + 4) * 4;                                                           \
     static bool set = false;                                                                                           \
     if (!set) { IEF_TRY(set_smem(attn_fwd_mma_kernel<DH_>, smem)); set = true; }                                       \
     attn_fwd_mma_kernel<DH_><<<grid, kThreads, smem, stream>>>(qkv, out, lse, T, H, H * dh, qs, thr, ik, seed);         \
@@ -379,7 +433,7 @@ int attn_train_bwd_mma(const float* qkv, const float* dout, const float* lse, co
   const dim3 grid((T + BQ - 1) / BQ, H, B);
 #define IEF_BWD(DH_)                                                                                                            \
   {                                                                                                                              \
-    const size_t smem = size_t(2 * BQ + 2 * BC) * (DH_ + 4) * 4 + 2 * BC * 4;                                                    \
+    const size_t smem = size_t(2 * BQ + 4 * BC) * (DH_ + 4) * 4 + 4 * BC * 4;                                                    \
     static bool set = false;                                                                                                     \
     if (!set) {                                                                                                                  \
       IEF_TRY(set_smem(attn_bwd_q_mma_kernel<DH_>, smem));                                                                       \
