@@ -6,7 +6,8 @@ The reference's loop builds its loss in the CALLER from `outputs['logits']` (thr
 contract is: the forward's outputs carry a grad_fn, and backward turns the gradients of those outputs into gradients of
 the 78 parameters.  `ForwardFn` is that autograd node.  Its forward is the model composed from the library's stand-alone
 operators (tcgen05 GEMMs with the 3-term bf16 split - gradients need fp32's exponent range, fp16 operands would flush
-them - fp32 attention / LayerNorm / fusion kernels) keeping what the backward needs; its backward runs entirely in
+them - the 3xTF32 tensor-core training attention of csrc/train_attn_mma.cu, fp32 LayerNorm / fusion kernels) keeping what
+the backward needs; its backward runs entirely in
 libiefvad.so kernels too: dgrad = linear(dY, W^T), wgrad = linear(dY^T, X^T) on the same tcgen05 GEMM, attention /
 LayerNorm / fusion / ReLU backward kernels of csrc/train.cu.  torch only owns the buffers and the autograd graph.
 
