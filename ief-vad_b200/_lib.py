@@ -72,6 +72,7 @@ _SIGS = {
     "iefvad_quickgelu": (_i, [_vp, _i64, _vp, _vp]),
     "iefvad_axpy": (_i, [_vp, _vp, _f, _i64, _vp]),
     "iefvad_outer": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "iefvad_wgrad": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp]),
     "iefvad_transpose": (_i, [_vp, _i64, _i, _vp, _i64, _vp]),
     "iefvad_clas2_bwd": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp]),
     "iefvad_locmap_proposals": (_i, [_vp, _vp, _vp, _i64, _i, _i] + [_vp] * 5),

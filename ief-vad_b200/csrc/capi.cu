@@ -829,6 +829,44 @@ int iefvad_transpose(const float* src, int64_t rows, int cols, float* dst, int64
   return transpose_f32(src, rows, cols, dst, ld_dst, static_cast<cudaStream_t>(stream));
 }
 
+int iefvad_wgrad(const float* dy, const float* x, int64_t rows, int out_f, int in_f, float alpha, float* dw, void* stream) {
+  IEF_CHECK(dy && x && dw, "iefvad_wgrad: null argument");
+  IEF_CHECK(rows > 0 && rows < (1LL << 31) && out_f % 32 == 0 && in_f % 32 == 0, "iefvad_wgrad: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  IEF_TRY(current_sms(&sms));
+  const int64_t Mp = (rows + 63) / 64 * 64;
+  Scratch sc(st);
+  void *yh, *yl, *xh, *xl;
+  IEF_TRY(sc.get(&yh, size_t(out_f) * Mp * 2));
+  IEF_TRY(sc.get(&yl, size_t(out_f) * Mp * 2));
+  IEF_TRY(sc.get(&xh, size_t(in_f) * Mp * 2));
+  IEF_TRY(sc.get(&xl, size_t(in_f) * Mp * 2));
+  // both operands go from row-major fp32 straight to the K-major bf16 hi / lo form the GEMM reads: one pass each instead
+  // of a transposition to fp32 followed by the conversion
+  IEF_TRY(transpose_split(dy, rows, out_f, (bf16*)yh, (bf16*)yl, Mp, st));
+  IEF_TRY(transpose_split(x, rows, in_f, (bf16*)xh, (bf16*)xl, Mp, st));
+  GemmTcArgs g;
+  g.A_hi = (bf16*)yh; g.A_lo = (bf16*)yl; g.W_hi = (bf16*)xh; g.W_lo = (bf16*)xl;
+  g.M = out_f; g.N = in_f; g.K = int(Mp); g.lda = int(Mp); g.ldw = int(Mp); g.nsplit = 3;
+  EpiParams ep;
+  ep.alpha = alpha; ep.out_f32 = dw; ep.ld_f32 = in_f;
+  if (out_f % 256 == 0 && in_f % 256 == 0 && Mp >= 4096 && (out_f / 256) * (in_f / 256) * 2 <= sms / 2) {
+    int S = (sms / 2) / ((out_f / 256) * (in_f / 256));
+    while (S > 1 && (Mp / 64) % S != 0) --S;
+    if (S > 1) {
+      void* part;
+      IEF_TRY(sc.get(&part, size_t(S) * out_f * in_f * 4));
+      ep.alpha = 1.f;
+      ep.out_f32 = static_cast<float*>(part);
+      g.ksplit = S; g.force_bn = 256; g.force_cg = 2;
+      IEF_TRY(gemm_tc(g, ep, sms, st));
+      return sum_slices(static_cast<const float*>(part), S, int64_t(out_f) * in_f, alpha, dw, sms, st);
+    }
+  }
+  return gemm_tc(g, ep, sms, st);
+}
+
 int iefvad_clas2_bwd(const float* logits, const float* means, const float* labels, int64_t label_stride, const int32_t* idx,
                      int64_t B, int64_t T, int kmax, const float* g_loss, float* dlogits, void* stream) {
   IEF_CHECK(logits && means && labels && idx && dlogits, "iefvad_clas2_bwd: null argument");

@@ -420,6 +420,32 @@ transpose_kernel(const float* __restrict__ src, long long rows, int cols, float*
   }
 }
 
+// the same transposition straight into the GEMM's operand format: bf16 hi = bf16(x), lo = bf16(x - hi), [cols, ld_dst]
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ src, long long rows, int cols, bf16* __restrict__ dst_hi, bf16* __restrict__ dst_lo,
+                       long long ld_dst) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const long long r = r0 + k;
+    const int c = c0 + tx;
+    tile[k][tx] = (r < rows && c < cols) ? src[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k;
+    const long long r = r0 + tx;
+    if (c < cols && r < ld_dst) {
+      bf16 h, l;
+      split_bf16(tile[tx][k], h, l);
+      dst_hi[(long long)c * ld_dst + r] = h;
+      dst_lo[(long long)c * ld_dst + r] = l;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- CLAS2 backward (train/loss.py:18-30)
 // loss = mean_b BCE(v_b, y_b), v_b = mean of the k_b largest sigmoid(logits[b, :len_b]), k_b = int(len_b / 16 + 1).
 // idx [B, kmax]: the chosen positions (-1 padded) from the forward's top-k kernel.
@@ -582,6 +608,16 @@ int transpose_f32(const float* src, long long rows, int cols, float* dst, long l
   if (rows == 0 || cols == 0) return IEFVAD_OK;
   const dim3 grid(unsigned((ld_dst + 31) / 32), unsigned((cols + 31) / 32));
   transpose_kernel<<<grid, 256, 0, stream>>>(src, rows, cols, dst, ld_dst);
+  count_launches(1);
+  IEF_CUDA(cudaGetLastError());
+  return IEFVAD_OK;
+}
+
+int transpose_split(const float* src, long long rows, int cols, bf16* dst_hi, bf16* dst_lo, long long ld_dst, cudaStream_t stream) {
+  IEF_CHECK(ld_dst >= rows, "transpose_split: ld_dst %lld < rows %lld", ld_dst, rows);
+  if (rows == 0 || cols == 0) return IEFVAD_OK;
+  const dim3 grid(unsigned((ld_dst + 31) / 32), unsigned((cols + 31) / 32));
+  transpose_split_kernel<<<grid, 256, 0, stream>>>(src, rows, cols, dst_hi, dst_lo, ld_dst);
   count_launches(1);
   IEF_CUDA(cudaGetLastError());
   return IEFVAD_OK;

@@ -34,6 +34,8 @@ int quickgelu(const float* x, long long n, float* out, int num_sms, cudaStream_t
 int axpy(float* y, const float* x, float alpha, long long n, int num_sms, cudaStream_t stream);
 int outer(const float* a, const float* w, long long rows, int D, float* out, int num_sms, cudaStream_t stream);
 int transpose_f32(const float* src, long long rows, int cols, float* dst, long long ld_dst, cudaStream_t stream);
+// dst_hi / dst_lo [cols, ld_dst] = bf16 hi / lo split of src^T (src [rows, cols] fp32), columns [rows, ld_dst) zero
+int transpose_split(const float* src, long long rows, int cols, bf16* dst_hi, bf16* dst_lo, long long ld_dst, cudaStream_t stream);
 int clas2_bwd(const float* logits, const float* means, const float* labels, long long label_stride, const int* idx, int B, int T,
               int kmax, const float* g_loss, float* dlogits, cudaStream_t stream);
 

@@ -308,6 +308,17 @@ def transpose(x, pad_to: int = 1):
     return out
 
 
+def wgrad(dy, x, alpha: float = 1.0):
+    """dW [out, in] = alpha * dy^T @ x for dy [rows, out], x [rows, in]."""
+    dy, x = _f32c(dy, "wgrad"), _f32c(x, "wgrad")
+    rows, out_f = dy.shape
+    in_f = x.shape[1]
+    dw = torch.empty((out_f, in_f), dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.lib.iefvad_wgrad(dy.data_ptr(), x.data_ptr(), rows, out_f, in_f, alpha, dw.data_ptr(), _stream(dy)))
+    return dw
+
+
 def clas2_bwd(logits, means, labels, idx, g_loss=None):
     x = _f32c(logits, "clas2_bwd")
     B, T = x.shape[0], x.shape[1]

@@ -36,9 +36,10 @@ def _dgrad(dy, w, resid=None, alpha=1.0):
     return _lin(dy, ops.transpose(w), None, resid=resid, alpha=alpha)
 
 
-def _wgrad(dy_t, x, alpha=1.0):
-    """dW [out, in] = alpha * dY^T . X from the transposed gradient dy_t [out, Mp] (rows zero-padded to a multiple of 64)."""
-    return _lin(dy_t, ops.transpose(x, pad_to=64), None, alpha=alpha)
+def _wgrad(dy, x, alpha=1.0):
+    """dW [out, in] = alpha * dY^T . X from row-major dY [M, out], X [M, in] (iefvad_wgrad: both operands transposed straight
+    into the GEMM's bf16 hi / lo form, split-K over the rows)."""
+    return ops.wgrad(dy, x, alpha)
 
 
 def param_list(temporal) -> List[torch.nn.Parameter]:
@@ -141,12 +142,11 @@ class ForwardFn(torch.autograd.Function):
             pi -= 4
             w1, w2 = params[pi], params[pi + 2]
             h, x = saved.pop(), saved.pop()
-            dx_t = ops.transpose(dx, pad_to=64)
             grads[pi + 3] = ops.axpy_(torch.zeros(D, dtype=torch.float32, device=dx.device), ops.colsum(dx), -lam)
-            grads[pi + 2] = _wgrad(dx_t, h, alpha=-lam)
+            grads[pi + 2] = _wgrad(dx, h, alpha=-lam)
             dz = ops.relu_bwd(_dgrad(dx, w2, alpha=-lam), h)
             grads[pi + 1] = ops.colsum(dz)
-            grads[pi] = _wgrad(ops.transpose(dz, pad_to=64), x)
+            grads[pi] = _wgrad(dz, x)
             dx = _dgrad(dz, w1, resid=dx)
         # ---- fusion (:130-144): dx is the gradient of `fused`
         d_mu_i, d_mu_e, d_lv_i, d_lv_e = ops.fuse_bwd(mu_i, mu_e, lv_i, lv_e, dx, g_wi, g_we, g_mu_i, g_mu_e, g_lv_i, g_lv_e,
@@ -157,9 +157,9 @@ class ForwardFn(torch.autograd.Function):
             base = mi * (6 * L + 6)
             ph = base + 6 * L + 2                      # mu.weight, mu.bias, logvar.weight, logvar.bias
             e = saved.pop()
-            grads[ph] = _wgrad(ops.transpose(d_mu, pad_to=64), e)
+            grads[ph] = _wgrad(d_mu, e)
             grads[ph + 1] = ops.colsum(d_mu)
-            grads[ph + 2] = _wgrad(ops.transpose(d_lv, pad_to=64), e)
+            grads[ph + 2] = _wgrad(d_lv, e)
             grads[ph + 3] = ops.colsum(d_lv)
             d_e = _dgrad(d_lv, params[ph + 2], resid=_dgrad(d_mu, params[ph]))
             x_w = saved.pop()
@@ -169,11 +169,10 @@ class ForwardFn(torch.autograd.Function):
                 w_in, w_o, g = params[p0], params[p0 + 2], params[p0 + 4]
                 y, lse, ctx_, qkv, x = saved.pop(), saved.pop(), saved.pop(), saved.pop(), saved.pop()
                 dy, grads[p0 + 4], grads[p0 + 5] = ops.layernorm_bwd(y, g, dxm)
-                dy_t = ops.transpose(dy, pad_to=64)
-                grads[p0 + 2] = _wgrad(dy_t, ctx_)
+                grads[p0 + 2] = _wgrad(dy, ctx_)
                 grads[p0 + 3] = ops.colsum(dy)
                 dqkv = ops.attention_train_bwd(qkv, ctx_, _dgrad(dy, w_o), lse, B, T, H, p_drop, seed + 1000 * mi + i)
-                grads[p0] = _wgrad(ops.transpose(dqkv, pad_to=64), x)
+                grads[p0] = _wgrad(dqkv, x)
                 grads[p0 + 1] = ops.colsum(dqkv)
                 dxm = _dgrad(dqkv, w_in, resid=dy)     # residual path + attention path
         assert not saved

@@ -339,6 +339,9 @@ int iefvad_fuse_bwd(const float* mu_i, const float* mu_e, const float* logvar_i,
                     const float* g_wi, const float* g_we, const float* g_mu_i, const float* g_mu_e, const float* g_logvar_i,
                     const float* g_logvar_e, int64_t n, float factor, float epsilon, float* d_mu_i, float* d_mu_e,
                     float* d_logvar_i, float* d_logvar_e, void* stream);
+/* Weight gradient of a Linear: dw [out_f, in_f] = alpha * dy^T . x for dy [rows, out_f], x [rows, in_f] (row-major fp32), with
+ * the 3-term bf16 split of the forward GEMMs (fp32's exponent range, ~16 mantissa bits) and split-K over the rows. */
+int iefvad_wgrad(const float* dy, const float* x, int64_t rows, int out_f, int in_f, float alpha, float* dw, void* stream);
 int iefvad_quickgelu(const float* x, int64_t n, float* out, void* stream);   /* model/module.py:15-17: x * sigmoid(1.702 x) */
 int iefvad_relu_bwd(const float* dh, const float* h, int64_t n, float* out, void* stream);      /* out = h > 0 ? dh : 0 */
 int iefvad_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);                /* y += alpha x */
