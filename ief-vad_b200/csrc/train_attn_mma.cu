@@ -105,7 +105,9 @@ __device__ __forceinline__ void mma_rows(float (&acc)[4][4], const uint32_t* til
 
 // out[nd] (16 x 8 each, nd < DH / 8) += W . X, W = four C tiles (16 x 32, contraction index renamed as above), X = rows of a
 // shared-memory tile [32, DH]
-template <int DH>
+// XSPLIT = false: X as single TF32 values - measured on the backward products (dq, dk, dv): 0.9 ms of the step faster, but the
+// full-size gradient test then fails its 1e-3 bound, so every call site keeps the (hi, lo) pairs
+template <int DH, bool XSPLIT = true>
 __device__ __forceinline__ void mma_cols(float (&out)[DH / 8][4], const float (&w)[4][4], const uint32_t* tile_x, int g, int t) {
   constexpr int P = DH + 4;
 #pragma unroll
@@ -119,12 +121,19 @@ __device__ __forceinline__ void mma_cols(float (&out)[DH / 8][4], const float (&
     split_tf32(__float_as_uint(w[j][3]), ah[3], al[3]);
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd) {
-      uint32_t bh0, bl0, bh1, bl1;
-      split_tf32(tile_x[(j * 8 + 2 * t) * P + nd * 8 + g], bh0, bl0);
-      split_tf32(tile_x[(j * 8 + 2 * t + 1) * P + nd * 8 + g], bh1, bl1);
-      mma_tf32(out[nd], al, bh0, bh1);
-      mma_tf32(out[nd], ah, bl0, bl1);
-      mma_tf32(out[nd], ah, bh0, bh1);
+      if (XSPLIT) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(tile_x[(j * 8 + 2 * t) * P + nd * 8 + g], bh0, bl0);
+        split_tf32(tile_x[(j * 8 + 2 * t + 1) * P + nd * 8 + g], bh1, bl1);
+        mma_tf32(out[nd], al, bh0, bh1);
+        mma_tf32(out[nd], ah, bl0, bl1);
+        mma_tf32(out[nd], ah, bh0, bh1);
+      } else {
+        const uint32_t b0 = to_tf32(__uint_as_float(tile_x[(j * 8 + 2 * t) * P + nd * 8 + g]));
+        const uint32_t b1 = to_tf32(__uint_as_float(tile_x[(j * 8 + 2 * t + 1) * P + nd * 8 + g]));
+        mma_tf32(out[nd], al, b0, b1);
+        mma_tf32(out[nd], ah, b0, b1);
+      }
     }
   }
 }
