@@ -15,9 +15,10 @@
 //   per-row partial sums through distributed shared memory.  Per tile an epilogue warp (32 rows x 128 columns, thread ==
 //   row) runs
 //     pass 1  tcgen05.ld accumulator chunk -> + bias -> y back into TMEM (tcgen05.st), accumulating the shifted sums of
-//             its part; st.shared::cluster of the record into the three CTAs that own these rows, one
-//             mbarrier.arrive.release.cluster per destination
-//     merge   wait (local mbarrier, 6 arrivals: 3 column tiles x 2 warps per row quarter), merge the parts in part order
+//             its part; the record goes into the three CTAs that own these rows with st.async ... complete_tx on THEIR
+//             mbarrier (no fence on the sending side)
+//     merge   wait on the local mbarrier (one expect_tx of 6 records x 32 lanes: 3 column tiles x 2 warps per row quarter),
+//             merge the parts in part order
 //     pass 2  tcgen05.ld y -> normalise -> fp16 (hi [, lo]) boxes -> TMA stores (or row-mapped stores)
 // * The sixteen epilogue warps form TWO TEAMS of eight; team t owns accumulator buffer t and the tiles of its parity, so
 //   while one team waits for the exchange (or for its accumulator) the other one computes, and every scheduler holds
