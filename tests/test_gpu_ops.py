@@ -160,3 +160,27 @@ def test_classifier(ops):
     assert logits.shape == (5, 77, 1)
     assert O.max_norm_err(logits.cpu().numpy(), ref) < 1e-5
     assert O.max_norm_err(scores.cpu().numpy(), O.sigmoid(ref[..., 0])) < 1e-5
+
+
+@pytest.mark.parametrize("rows,out_f,in_f", [(16384, 768, 768), (4096, 768, 2304), (1000, 256, 768), (333, 64, 96)])
+def test_wgrad_split_k_matches_fp64(ops, rows, out_f, in_f):
+    """iefvad_wgrad: dW = alpha * dY^T X (train/ucf_train.py:105's backward through every Linear) - operands transposed straight
+    into the bf16 hi / lo form, K slices as extra row tiles where the output is small, slices summed in fixed order."""
+    g = torch.Generator().manual_seed(rows + in_f)
+    dy = torch.randn(rows, out_f, generator=g) * torch.logspace(-6, 0, out_f)     # gradients span many decades
+    x = torch.randn(rows, in_f, generator=g)
+    got = ops.wgrad(dy.cuda(), x.cuda(), alpha=-0.5)
+    again = ops.wgrad(dy.cuda(), x.cuda(), alpha=-0.5)
+    ref = -0.5 * dy.double().T @ x.double()
+    assert torch.equal(got, again)                                               # no atomics: run-to-run identical
+    err = (got.double().cpu() - ref).abs().max(dim=1).values / ref.abs().max(dim=1).values
+    assert err.max().item() < 5e-5, err.max().item()                            # 3-term bf16 split, per output row (decade)
+
+
+def test_linear_long_k_takes_the_split_k_path_and_matches(ops):
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(768, 16384, generator=g)
+    b = torch.randn(768, 16384, generator=g)
+    got = ops.linear(a.cuda(), b.cuda(), plan="split").double().cpu()
+    ref = a.double() @ b.double().T
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < TOL["split"]
